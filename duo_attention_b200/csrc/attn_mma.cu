@@ -1,0 +1,536 @@
+// Mixed-head attention, bandwidth ("decode") kernel family.
+//
+// One launch serves BOTH head classes of a layer (replaces the two flash_attn_func launches +
+// torch.cat of duo_attn/patch/llama.py:234-267 / :374-421):
+//   * retrieval kv-heads stream the whole head-major KV cache, split along the key axis over
+//     enough CTAs to fill the 148 SMs; partial (m, l, O) go to a workspace and the LAST CTA of a
+//     head to arrive merges them in the same launch (no second kernel);
+//   * streaming kv-heads read only the valid sink+ring slots plus the staged chunk.
+// K/V tiles (64 keys x 128 dims, K and V) are fetched by TMA (cp.async.bulk.tensor, 128B
+// swizzle) into a 3-stage mbarrier pipeline; QK^T and PV run on mma.sync m16n8k16 with fp32
+// accumulation reading the swizzled tiles through ldmatrix.  The GQA group (and up to a few
+// query tokens) is packed into the 16-row MMA M dimension so each K/V byte is read from HBM
+// exactly once.  The kernel is HBM-bound by design; the tensor-core prefill kernel for large
+// chunks lives in attn_tc.cu.
+//
+// Variants:  KEY_WARPS=4 -> 16 packed rows per CTA, the 4 warps split the keys of each tile
+//                           (decode: rows = group * q_len <= 16)
+//            KEY_WARPS=1 -> 64 packed rows per CTA, each warp owns 16 rows (small chunks and the
+//                           generic fallback for ragged prefill shapes)
+#include "duo_common.cuh"
+
+namespace duo {
+
+constexpr int TILE = 64;                             // keys per pipeline stage
+constexpr int STAGES = 3;
+constexpr int KV_BOX_BYTES = TILE * 128;             // one 64-wide half of a K or V tile
+constexpr int STAGE_BYTES = 4 * KV_BOX_BYTES;        // K lo, K hi, V lo, V hi = 32 KB
+constexpr int ATTN_THREADS = 128;
+
+struct AttnParams {
+  const void* q;
+  void* out;
+  long long q_tok_stride;    // elements
+  long long q_batch_stride;  // elements
+  long long out_batch_stride;
+  int q_len, n_q_heads, group, n_full, n_stream, batch;
+  int sink, recent, W;
+  long long full_len, total, lo;
+  float scale_log2;
+  int splits_full;       // key splits for retrieval heads
+  int keys_per_split;    // multiple of TILE
+  int n_rb;              // row blocks per kv head
+  int cache_scan;        // streaming: slots [0, cache_scan) are scanned
+  float* ws_o;           // [batch][n_full][n_rb][splits][ROWS][128]
+  float* ws_ml;          // [batch][n_full][n_rb][splits][ROWS][2]
+  int* counters;         // [batch][n_full][n_rb]
+};
+
+template <typename T, int KEY_WARPS>
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
+duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_constant__ CUtensorMap map_fv,
+                    const __grid_constant__ CUtensorMap map_rk, const __grid_constant__ CUtensorMap map_rv,
+                    const AttnParams p) {
+  constexpr int ROW_WARPS = 4 / KEY_WARPS;
+  constexpr int ROWS = 16 * ROW_WARPS;
+  constexpr int KPW = TILE / KEY_WARPS;  // keys per warp per tile
+  constexpr int NT = KPW / 8;            // S n-tiles per warp
+  using Op = MmaOp<T>;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int b = blockIdx.y;
+
+  // ---- decode the work item ------------------------------------------------------------------
+  const int n_full_items = p.n_full * p.n_rb * p.splits_full;
+  int kvh, rb, split;
+  bool is_full;
+  if ((int)blockIdx.x < n_full_items) {
+    is_full = true;
+    int x = blockIdx.x;
+    split = x % p.splits_full;
+    x /= p.splits_full;
+    rb = p.n_rb - 1 - (x % p.n_rb);  // heavy (late) row blocks first
+    kvh = x / p.n_rb;
+  } else {
+    is_full = false;
+    int x = blockIdx.x - n_full_items;
+    rb = p.n_rb - 1 - (x % p.n_rb);
+    kvh = p.n_full + x / p.n_rb;
+    split = 0;
+  }
+  const int rows_total = p.group * p.q_len;
+  const int row0 = rb * ROWS;
+  const int rows_here = min(ROWS, rows_total - row0);
+  const int tok_max = (row0 + rows_here - 1) / p.group;
+
+  // key segments [a0,a1) (cache) and [b0,b1) (staged chunk, streaming heads only)
+  long long a0, a1, b0 = 0, b1 = 0;
+  long long base;  // key j visible to token t  <=>  j <= base + t
+  if (is_full) {
+    base = p.full_len;
+    long long nkeys = p.full_len + tok_max + 1;
+    a0 = (long long)split * p.keys_per_split;
+    a1 = min(nkeys, a0 + (long long)p.keys_per_split);
+    if (a1 < a0) a1 = a0;
+  } else {
+    base = p.W;
+    a0 = 0;
+    a1 = p.cache_scan;
+    b0 = p.W;
+    b1 = (long long)p.W + tok_max + 1;
+  }
+  const int nA = (int)((a1 - a0 + TILE - 1) / TILE);
+  const int nB = (int)((b1 - b0 + TILE - 1) / TILE);
+  const int n_tiles = nA + nB;
+  const CUtensorMap* mk = is_full ? &map_fk : &map_rk;
+  const CUtensorMap* mv = is_full ? &map_fv : &map_rv;
+  const int head_coord = is_full ? (b * p.n_full + kvh) : (b * p.n_stream + (kvh - p.n_full));
+
+  if (tid == 0) {
+    prefetch_tmap(mk);
+    prefetch_tmap(mv);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto tile_start = [&](int i) -> long long { return i < nA ? a0 + (long long)i * TILE : b0 + (long long)(i - nA) * TILE; };
+  auto issue = [&](int i) {
+    const int s = i % STAGES;
+    uint8_t* dst = smem + s * STAGE_BYTES;
+    const int j0 = (int)tile_start(i);
+    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+    tma_load_3d(dst, mk, &full_bar[s], 0, j0, head_coord);
+    tma_load_3d(dst + KV_BOX_BYTES, mk, &full_bar[s], 64, j0, head_coord);
+    tma_load_3d(dst + 2 * KV_BOX_BYTES, mv, &full_bar[s], 0, j0, head_coord);
+    tma_load_3d(dst + 3 * KV_BOX_BYTES, mv, &full_bar[s], 64, j0, head_coord);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < STAGES - 1 && i < n_tiles; ++i) issue(i);
+  }
+
+  // ---- Q fragments (registers, loaded once) -----------------------------------------------------
+  const int wrow = (KEY_WARPS == 1) ? warp * 16 : 0;  // first packed row of this warp inside the CTA
+  const int wkey = (KEY_WARPS == 1) ? 0 : warp * KPW; // first key of this warp inside a tile
+  uint32_t qa[8][4];
+  int tok_r[2];
+  {
+    const T* qb = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_batch_stride;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int R = row0 + wrow + g + hf * 8;
+      const bool ok = R < rows_total;
+      const int tok = ok ? R / p.group : 0;
+      const int hq = kvh * p.group + (ok ? R % p.group : 0);
+      tok_r[hf] = ok ? tok : -1;
+      const T* src = qb + (long long)tok * p.q_tok_stride + (long long)hq * kHeadDim;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        uint32_t v0 = 0, v1 = 0;
+        if (ok) {
+          v0 = *reinterpret_cast<const uint32_t*>(src + kk * 16 + 2 * t4);
+          v1 = *reinterpret_cast<const uint32_t*>(src + kk * 16 + 8 + 2 * t4);
+        }
+        qa[kk][hf] = v0;
+        qa[kk][hf + 2] = v1;
+      }
+    }
+  }
+
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+
+  // per-lane ldmatrix address components
+  const int lrow = lane & 7;
+  const int lmat = lane >> 3;  // 0..3
+
+  for (int i = 0; i < n_tiles; ++i) {
+    __syncthreads();  // everyone is done with tile i-1 -> its stage may be refilled
+    if (tid == 0 && i + STAGES - 1 < n_tiles) issue(i + STAGES - 1);
+    const int s = i % STAGES;
+    mbar_wait(&full_bar[s], (i / STAGES) & 1);
+    const uint32_t sK = smem_u32(smem + s * STAGE_BYTES);
+    const uint32_t sV = sK + 2 * KV_BOX_BYTES;
+    const long long j0 = tile_start(i);
+    const long long jend = (i < nA) ? a1 : b1;
+
+    // ---- S = Q K^T ------------------------------------------------------------------------------
+    float sc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+      for (int pr = 0; pr < NT / 2; ++pr) {
+        const int krow = wkey + pr * 16 + (lmat >> 1) * 8 + lrow;
+        const int cc = kk * 2 + (lmat & 1);  // 16-byte chunk index 0..15 along head_dim
+        const uint32_t addr = sK + (cc >> 3) * KV_BOX_BYTES + krow * 128 + (((cc & 7) ^ (krow & 7)) << 4);
+        uint32_t r0, r1, r2, r3;
+        ldsm_x4(r0, r1, r2, r3, addr);
+        Op::run(sc[2 * pr], qa[kk], r0, r1);
+        Op::run(sc[2 * pr + 1], qa[kk], r2, r3);
+      }
+    }
+
+    // ---- mask + online softmax ----------------------------------------------------------------
+    const long long kfirst = j0 + wkey;
+    const int tmin = (row0 + wrow) / p.group;
+    const bool need_mask = (kfirst + KPW > jend) || (kfirst + KPW - 1 > base + tmin) ||
+                           (!is_full && i < nA);  // rows beyond rows_here hold q == 0 and are never stored
+    if (need_mask) {
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long j = kfirst + n * 8 + 2 * t4 + (e & 1);
+          const int tk = tok_r[e >> 1];
+          bool vis = (tk >= 0) && (j < jend) && (j <= base + tk);
+          if (!is_full && j < p.W) vis = vis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
+          if (!vis) sc[n][e] = -INFINITY;
+        }
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      mx[0] = fmaxf(mx[0], fmaxf(sc[n][0], sc[n][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sc[n][2], sc[n][3]));
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 1));
+      mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 2));
+    }
+    float alpha[2], msc[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float m_new = fmaxf(m_run[hf], mx[hf]);
+      msc[hf] = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+      alpha[hf] = (m_run[hf] == -INFINITY) ? 0.f : fast_exp2(m_run[hf] * p.scale_log2 - msc[hf]);
+      m_run[hf] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pa[NT / 2][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float p0 = fast_exp2(sc[n][0] * p.scale_log2 - msc[0]);
+      const float p1 = fast_exp2(sc[n][1] * p.scale_log2 - msc[0]);
+      const float p2 = fast_exp2(sc[n][2] * p.scale_log2 - msc[1]);
+      const float p3 = fast_exp2(sc[n][3] * p.scale_log2 - msc[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      // accumulator layout of two adjacent n-tiles == A fragment of one k16 step
+      pa[n >> 1][(n & 1) * 2 + 0] = Op::pack(p0, p1);
+      pa[n >> 1][(n & 1) * 2 + 1] = Op::pack(p2, p3);
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) l_run[hf] = l_run[hf] * alpha[hf] + rs[hf];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      o[d][0] *= alpha[0];
+      o[d][1] *= alpha[0];
+      o[d][2] *= alpha[1];
+      o[d][3] *= alpha[1];
+    }
+
+    // ---- O += P V -------------------------------------------------------------------------------
+#pragma unroll
+    for (int k2 = 0; k2 < NT / 2; ++k2) {
+#pragma unroll
+      for (int q2 = 0; q2 < 8; ++q2) {
+        const int krow = wkey + k2 * 16 + (lmat & 1) * 8 + lrow;
+        const int cc = q2 * 2 + (lmat >> 1);
+        const uint32_t addr = sV + (cc >> 3) * KV_BOX_BYTES + krow * 128 + (((cc & 7) ^ (krow & 7)) << 4);
+        uint32_t r0, r1, r2, r3;
+        ldsm_x4_trans(r0, r1, r2, r3, addr);
+        Op::run(o[2 * q2], pa[k2], r0, r1);
+        Op::run(o[2 * q2 + 1], pa[k2], r2, r3);
+      }
+    }
+  }
+
+  // row sums live distributed over the 4 lanes of a quad
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    l_run[hf] += __shfl_xor_sync(0xffffffffu, l_run[hf], 1);
+    l_run[hf] += __shfl_xor_sync(0xffffffffu, l_run[hf], 2);
+  }
+
+  // ---- cross-warp merge (KEY_WARPS == 4): every warp holds partials for the same 16 rows ---------
+  __syncthreads();  // all TMA tiles consumed -> pipeline smem is free for reuse
+  float* sm_o = reinterpret_cast<float*>(smem);                 // [ROWS][128] merged, unnormalised
+  float* sm_ml = reinterpret_cast<float*>(smem + 64 * 1024);    // [ROWS][2]   (m in log2 units, l)
+  if constexpr (KEY_WARPS == 4) {
+    float* w_o = reinterpret_cast<float*>(smem) + 16 * 128;     // [4][16][128] behind the merged block
+    float* w_ml = sm_ml + 64;                                   // [4][16][2]
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int r = g + hf * 8;
+      if (t4 == 0) {
+        w_ml[(warp * 16 + r) * 2 + 0] = (m_run[hf] == -INFINITY) ? -INFINITY : m_run[hf] * p.scale_log2;
+        w_ml[(warp * 16 + r) * 2 + 1] = l_run[hf];
+      }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        float2 v = make_float2(o[d][hf * 2], o[d][hf * 2 + 1]);
+        *reinterpret_cast<float2*>(&w_o[(warp * 16 + r) * 128 + d * 8 + 2 * t4]) = v;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 16 * 128; idx += ATTN_THREADS) {
+      const int r = idx >> 7, d = idx & 127;
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, w_ml[(w * 16 + r) * 2]);
+      float acc = 0.f, ll = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = w_ml[(w * 16 + r) * 2];
+        const float f = (mw == -INFINITY) ? 0.f : fast_exp2(mw - mm);
+        acc += f * w_o[(w * 16 + r) * 128 + d];
+        ll += f * w_ml[(w * 16 + r) * 2 + 1];
+      }
+      sm_o[r * 128 + d] = acc;
+      if (d == 0) {
+        sm_ml[r * 2] = mm;
+        sm_ml[r * 2 + 1] = ll;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int r = wrow + g + hf * 8;
+      if (t4 == 0) {
+        sm_ml[r * 2 + 0] = (m_run[hf] == -INFINITY) ? -INFINITY : m_run[hf] * p.scale_log2;
+        sm_ml[r * 2 + 1] = l_run[hf];
+      }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        float2 v = make_float2(o[d][hf * 2], o[d][hf * 2 + 1]);
+        *reinterpret_cast<float2*>(&sm_o[r * 128 + d * 8 + 2 * t4]) = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  T* outb = reinterpret_cast<T*>(p.out) + (long long)b * p.out_batch_stride;
+  auto store_row_elem = [&](int r, int d, float v0, float v1) {
+    const int R = row0 + r;
+    const int tok = R / p.group;
+    const int hq = kvh * p.group + R % p.group;
+    T* dst = outb + ((long long)tok * p.n_q_heads + hq) * kHeadDim + d;
+    *reinterpret_cast<uint32_t*>(dst) = Op::pack(v0, v1);
+  };
+
+  const int nsplit = is_full ? p.splits_full : 1;
+  if (nsplit == 1) {
+    for (int idx = tid; idx < rows_here * 64; idx += ATTN_THREADS) {
+      const int r = idx >> 6, d = (idx & 63) * 2;
+      const float l = sm_ml[r * 2 + 1];
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      store_row_elem(r, d, sm_o[r * 128 + d] * inv, sm_o[r * 128 + d + 1] * inv);
+    }
+    return;
+  }
+
+  // ---- split-KV: publish the partial, last CTA of this (batch, head, row block) merges ------------
+  const long long item = ((long long)b * p.n_full + kvh) * p.n_rb + rb;
+  float* wo = p.ws_o + (item * p.splits_full + split) * (long long)(ROWS * 128);
+  float* wml = p.ws_ml + (item * p.splits_full + split) * (long long)(ROWS * 2);
+  for (int idx = tid; idx < rows_here * 32; idx += ATTN_THREADS) {
+    const int r = idx >> 5, d4 = (idx & 31) * 4;
+    *reinterpret_cast<float4*>(&wo[r * 128 + d4]) = *reinterpret_cast<const float4*>(&sm_o[r * 128 + d4]);
+  }
+  if (tid < rows_here * 2) wml[tid] = sm_ml[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(&p.counters[item], 1);
+    s_is_last = (prev == p.splits_full - 1);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const float* po = p.ws_o + item * p.splits_full * (long long)(ROWS * 128);
+  const float* pml = p.ws_ml + item * p.splits_full * (long long)(ROWS * 2);
+  for (int idx = tid; idx < rows_here * 64; idx += ATTN_THREADS) {
+    const int r = idx >> 6, d = (idx & 63) * 2;
+    float mm = -INFINITY;
+    for (int s2 = 0; s2 < p.splits_full; ++s2) mm = fmaxf(mm, __ldcg(&pml[(s2 * ROWS + r) * 2]));
+    float a0f = 0.f, a1f = 0.f, ll = 0.f;
+    for (int s2 = 0; s2 < p.splits_full; ++s2) {
+      const float ms = __ldcg(&pml[(s2 * ROWS + r) * 2]);
+      if (ms == -INFINITY) continue;
+      const float f = fast_exp2(ms - mm);
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(&po[((long long)s2 * ROWS + r) * 128 + d]));
+      a0f += f * v.x;
+      a1f += f * v.y;
+      ll += f * __ldcg(&pml[(s2 * ROWS + r) * 2 + 1]);
+    }
+    const float inv = ll > 0.f ? 1.f / ll : 0.f;
+    store_row_elem(r, d, a0f * inv, a1f * inv);
+  }
+  if (tid == 0) p.counters[item] = 0;  // leave the workspace ready for the next launch
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+constexpr int ATTN_SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+
+size_t mma_workspace_bytes(int batch, int n_kv, int group, int max_q_len) {
+  // The launcher never creates more than ~2 CTAs/SM worth of split partials (items * splits <= budget),
+  // each at most 64 rows x (128 + 2) floats; counters: one per (batch, kv head, row block).
+  const long long max_partials = 2 * 160 + 64;
+  const long long rows = (long long)group * max_q_len;
+  const long long items = (long long)batch * n_kv * ((rows + 15) / 16);
+  const long long o = max_partials * 64 * 128 * 4;
+  const long long ml = max_partials * 64 * 2 * 4;
+  const long long cnt = (items + 1) * 4;
+  return (size_t)(o + ml + cnt + 4096);
+}
+
+template <typename T, int KEY_WARPS>
+static int launch_variant(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride,
+                          void* out, int q_len, float scale, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream) {
+  const duo_layer_desc& d = L->d;
+  constexpr int ROWS = 16 * (4 / KEY_WARPS);
+  AttnParams p{};
+  p.q = q;
+  p.out = out;
+  p.q_tok_stride = q_row_stride;
+  p.q_batch_stride = q_row_stride * q_len;
+  const int n_q = (d.n_full + d.n_stream) * d.group;
+  p.out_batch_stride = (long long)q_len * n_q * kHeadDim;
+  p.q_len = q_len;
+  p.n_q_heads = n_q;
+  p.group = d.group;
+  p.n_full = d.n_full;
+  p.n_stream = d.n_stream;
+  p.batch = d.batch;
+  p.sink = d.sink;
+  p.recent = d.recent;
+  p.W = d.sink + d.recent;
+  p.full_len = st->full_len;
+  p.total = st->total;
+  p.lo = st->lo;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int rows = d.group * q_len;
+  p.n_rb = (rows + ROWS - 1) / ROWS;
+  // streaming cache scan range: slots [0, min(W, total)) can hold live tokens
+  p.cache_scan = (int)std::min<long long>(p.W, st->total);
+
+  // split the retrieval heads' keys so that the grid covers ~2 CTAs per SM
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int cached_dev = -1, cached_sms = 148;
+    if (cached_dev != dev) {
+      cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+      cached_dev = dev;
+    }
+    sm_count = cached_sms;
+  }
+  const long long nkeys = st->full_len + q_len;
+  int splits = 1;
+  if (d.n_full > 0) {
+    const int budget = 2 * sm_count;
+    const int base_ctas = d.batch * d.n_full * p.n_rb;
+    const int stream_ctas = d.batch * d.n_stream * p.n_rb;
+    int want = (budget - stream_ctas > 0 ? budget - stream_ctas : 1) / base_ctas;
+    if (want < 1) want = 1;
+    const long long max_by_len = (nkeys + 4 * TILE - 1) / (4 * TILE);  // >= 256 keys per split
+    splits = (int)std::min<long long>(want, std::max<long long>(1, max_by_len));
+    if (splits > 512) splits = 512;
+  }
+  long long kps = (nkeys + splits - 1) / splits;
+  kps = (kps + TILE - 1) / TILE * TILE;
+  if (kps < TILE) kps = TILE;
+  splits = (int)((nkeys + kps - 1) / kps);
+  if (splits < 1) splits = 1;
+  p.splits_full = splits;
+  p.keys_per_split = (int)kps;
+
+  const long long items = (long long)d.batch * d.n_full * p.n_rb;
+  const size_t need_o = (size_t)items * splits * ROWS * 128 * 4;
+  const size_t need_ml = (size_t)items * splits * ROWS * 2 * 4;
+  const size_t need_cnt = (size_t)(items + 1) * 4;
+  if (splits > 1) {
+    if (workspace == nullptr || workspace_bytes < need_o + need_ml + need_cnt + 256) {
+      set_error("duo_attention: workspace too small (%zu < %zu)", workspace_bytes, need_o + need_ml + need_cnt + 256);
+      return DUO_EWORKSPACE;
+    }
+  }
+  // counters first (they must stay zero between launches; O/ml partials need no initialisation)
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  p.counters = reinterpret_cast<int*>(ws);
+  const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
+  p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
+  p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
+
+  const int grid_x = d.n_full * p.n_rb * splits + d.n_stream * p.n_rb;
+  if (grid_x == 0) return DUO_OK;
+  auto kern = duo_attn_mma_kernel<T, KEY_WARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES));
+    attr_set = true;
+  }
+  // a layer without retrieval (or without streaming) heads still needs *some* valid descriptor object in
+  // the parameter slot; it is never dereferenced because no CTA of that class is launched.
+  const CUtensorMap& fk = L->has_full_maps ? L->maps.full_k64 : L->maps.ring_k64;
+  const CUtensorMap& fv = L->has_full_maps ? L->maps.full_v64 : L->maps.ring_v64;
+  const CUtensorMap& rk = L->has_ring_maps ? L->maps.ring_k64 : L->maps.full_k64;
+  const CUtensorMap& rv = L->has_ring_maps ? L->maps.ring_v64 : L->maps.full_v64;
+  kern<<<dim3(grid_x, d.batch), ATTN_THREADS, ATTN_SMEM_BYTES, stream>>>(fk, fv, rk, rv, p);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+int launch_attn_mma(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
+                    int q_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int rows = L->d.group * q_len;
+  if (L->d.dtype == DUO_DT_BF16) {
+    if (rows <= 16)
+      return launch_variant<__nv_bfloat16, 4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
+    return launch_variant<__nv_bfloat16, 1>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
+  } else {
+    if (rows <= 16)
+      return launch_variant<__half, 4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
+    return launch_variant<__half, 1>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
+  }
+}
+
+}  // namespace duo

@@ -1,0 +1,340 @@
+// KV-side kernels of the hot path: RoPE + cache append (+ INT4 quantise), streaming ring commit,
+// stand-alone INT4 quantise / dequantise.  All HBM-bound byte work: one warp per 128-element row,
+// 8-byte vector loads (a full row = one 256 B coalesced request), warp-shuffle reductions.
+//
+// Reference semantics restated here:
+//   RoPE (HF op order)       duo_attn/patch/llama.py:177-184 -> transformers apply_rotary_pos_emb
+//   RoPE (fp32, flashinfer)  duo_attn/patch/flashinfer_utils.py:29-59
+//   append                   duo_attn/patch/static_kv_cache.py:109-125, 252-263
+//   ring commit              duo_attn/patch/static_kv_cache.py:127-167 / llama.py:273-290
+//   INT4 K1 / K2             demo/quantize_int4.cu:73-144 / :9-42
+#include "duo_common.cuh"
+
+namespace duo {
+
+template <typename T>
+struct Cvt;
+template <>
+struct Cvt<__nv_bfloat16> {
+  __device__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <>
+struct Cvt<__half> {
+  __device__ static float to_f(__half v) { return __half2float(v); }
+  __device__ static __half from_f(float v) { return __float2half_rn(v); }
+};
+
+template <typename T>
+struct alignas(8) Vec4 {
+  T v[4];
+};
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// K1 arithmetic for one 128-element group held 4-per-lane (fp16-representable values in x[]).
+// Writes 2 packed bytes per lane; lane 0 writes scale / zero.
+__device__ __forceinline__ void quant_row_int4(const float (&x)[4], int lane, uint8_t* packed_row, __half* scale_p,
+                                               __half* zero_p) {
+  float mn = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
+  float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  const float scale = __fadd_rn(__fdiv_rn(__fsub_rn(mx, mn), 15.0f), 1e-8f);
+  const float zero = mn;
+  uint32_t q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float qf = __fdiv_rn(__fsub_rn(x[i], zero), scale);
+    qf = roundf(qf);
+    qf = fminf(fmaxf(qf, 0.0f), 15.0f);
+    q[i] = (uint32_t)qf;
+  }
+  const uint16_t two = (uint16_t)(((q[0] << 4) | q[1]) | (((q[2] << 4) | q[3]) << 8));
+  *reinterpret_cast<uint16_t*>(packed_row + 2 * lane) = two;
+  if (lane == 0) {
+    *scale_p = __float2half_rn(scale);
+    *zero_p = __float2half_rn(zero);
+  }
+}
+
+struct RopeAppendParams {
+  void* qkv;
+  long long row_stride;  // elements between consecutive tokens
+  const void* cos;
+  const void* sin;
+  int rope_mode;
+  int q_len, batch, n_q, n_kv, n_full, n_stream;
+  int W, ring_slots;  // sink+recent, sink+recent+stage_cap
+  long long full_cap, full_len;
+  int kv_int4;
+  void *full_k, *full_v, *ring_k, *ring_v;
+  __half *fks, *fkz, *fvs, *fvz, *rks, *rkz, *rvs, *rvz;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) rope_append_kernel(const RopeAppendParams p) {
+  const int lane = threadIdx.x & 31;
+  const int slots = p.n_q + 2 * p.n_kv;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total_rows = (long long)p.batch * p.q_len * slots;
+  if (wid >= total_rows) return;
+  const int slot = (int)(wid % slots);
+  const long long bt = wid / slots;
+  const int t = (int)(bt % p.q_len);
+  const int b = (int)(bt / p.q_len);
+
+  T* row = reinterpret_cast<T*>(p.qkv) + (bt * p.row_stride) + (long long)slot * kHeadDim;
+  Vec4<T> xv = *reinterpret_cast<const Vec4<T>*>(row + lane * 4);
+  const bool is_q = slot < p.n_q;
+  const bool is_k = !is_q && slot < p.n_q + p.n_kv;
+  const bool is_v = !is_q && !is_k;
+
+  float xo[4];  // values as they will be stored (already rounded to T)
+  if (!is_v && p.rope_mode != DUO_ROPE_NONE) {
+    // rotate_half partner: element i pairs with i +- 64  <=> lane +- 16
+    Vec4<T> pv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float mine = Cvt<T>::to_f(xv.v[i]);
+      const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+      pv.v[i] = Cvt<T>::from_f(lane < 16 ? -other : other);
+    }
+    if (p.rope_mode == DUO_ROPE_HF) {
+      const Vec4<T> cv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(p.cos) + (long long)t * kHeadDim + lane * 4);
+      const Vec4<T> sv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(p.sin) + (long long)t * kHeadDim + lane * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const T a = Cvt<T>::from_f(__fmul_rn(Cvt<T>::to_f(xv.v[i]), Cvt<T>::to_f(cv.v[i])));
+        const T r = Cvt<T>::from_f(__fmul_rn(Cvt<T>::to_f(pv.v[i]), Cvt<T>::to_f(sv.v[i])));
+        xv.v[i] = Cvt<T>::from_f(__fadd_rn(Cvt<T>::to_f(a), Cvt<T>::to_f(r)));
+      }
+    } else {
+      const float4 cv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.cos) + (long long)t * kHeadDim + lane * 4);
+      const float4 sv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.sin) + (long long)t * kHeadDim + lane * 4);
+      const float c[4] = {cv.x, cv.y, cv.z, cv.w};
+      const float s[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        xv.v[i] = Cvt<T>::from_f(Cvt<T>::to_f(xv.v[i]) * c[i] + Cvt<T>::to_f(pv.v[i]) * s[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xo[i] = Cvt<T>::to_f(xv.v[i]);
+
+  if (is_q) {
+    if (p.rope_mode != DUO_ROPE_NONE) *reinterpret_cast<Vec4<T>*>(row + lane * 4) = xv;
+    return;
+  }
+  const int h = is_k ? slot - p.n_q : slot - p.n_q - p.n_kv;
+  const bool full = h < p.n_full;
+  long long dst_row;  // row index inside the destination tensor
+  if (full)
+    dst_row = ((long long)b * p.n_full + h) * p.full_cap + p.full_len + t;
+  else
+    dst_row = ((long long)b * p.n_stream + (h - p.n_full)) * p.ring_slots + p.W + t;
+  void* base = full ? (is_k ? p.full_k : p.full_v) : (is_k ? p.ring_k : p.ring_v);
+  if (!p.kv_int4) {
+    *reinterpret_cast<Vec4<T>*>(reinterpret_cast<T*>(base) + dst_row * kHeadDim + lane * 4) = xv;
+  } else {
+    __half* sc = full ? (is_k ? p.fks : p.fvs) : (is_k ? p.rks : p.rvs);
+    __half* zp = full ? (is_k ? p.fkz : p.fvz) : (is_k ? p.rkz : p.rvz);
+    quant_row_int4(xo, lane, reinterpret_cast<uint8_t*>(base) + dst_row * (kHeadDim / 2), sc + dst_row, zp + dst_row);
+  }
+}
+
+int launch_rope_append(const duo_layer* L, const duo_cache_state* st, void* qkv, long long row_stride, const void* cos,
+                       const void* sin, int rope_mode, int q_len, cudaStream_t stream) {
+  const duo_layer_desc& d = L->d;
+  RopeAppendParams p{};
+  p.qkv = qkv;
+  p.row_stride = row_stride;
+  p.cos = cos;
+  p.sin = sin;
+  p.rope_mode = rope_mode;
+  p.q_len = q_len;
+  p.batch = d.batch;
+  p.n_kv = d.n_full + d.n_stream;
+  p.n_q = p.n_kv * d.group;
+  p.n_full = d.n_full;
+  p.n_stream = d.n_stream;
+  p.W = d.sink + d.recent;
+  p.ring_slots = p.W + d.stage_cap;
+  p.full_cap = d.full_cap;
+  p.full_len = st->full_len;
+  p.kv_int4 = d.kv_format == DUO_KV_INT4;
+  p.full_k = d.full_k;
+  p.full_v = d.full_v;
+  p.ring_k = d.ring_k;
+  p.ring_v = d.ring_v;
+  p.fks = (__half*)d.full_k_scale;
+  p.fkz = (__half*)d.full_k_zero;
+  p.fvs = (__half*)d.full_v_scale;
+  p.fvz = (__half*)d.full_v_zero;
+  p.rks = (__half*)d.ring_k_scale;
+  p.rkz = (__half*)d.ring_k_zero;
+  p.rvs = (__half*)d.ring_v_scale;
+  p.rvz = (__half*)d.ring_v_zero;
+  const long long rows = (long long)d.batch * q_len * (p.n_q + 2 * p.n_kv);
+  const int wpb = 8;
+  const long long blocks = (rows + wpb - 1) / wpb;
+  if (blocks == 0) return DUO_OK;
+  if (d.dtype == DUO_DT_BF16)
+    rope_append_kernel<__nv_bfloat16><<<(unsigned)blocks, wpb * 32, 0, stream>>>(p);
+  else
+    rope_append_kernel<__half><<<(unsigned)blocks, wpb * 32, 0, stream>>>(p);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ring commit: staged chunk rows -> sink / ring slots
+// ---------------------------------------------------------------------------------------------
+struct CommitParams {
+  uint8_t *ring_k, *ring_v;
+  __half *rks, *rkz, *rvs, *rvz;
+  int row_bytes;  // 256 (16-bit) or 64 (int4)
+  int kv_int4;
+  int batch, n_stream, ring_slots, W, sink, recent, q_len;
+  long long total;
+  int n_cand;      // candidate chunk rows per head: sinks first, then the tail
+  int n_sink_new;  // chunk rows [0, n_sink_new) land in sink slots
+  int tail_start;  // chunk rows [tail_start, q_len) land in the ring
+};
+
+__global__ void __launch_bounds__(256) stream_commit_kernel(const CommitParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total_rows = (long long)p.batch * p.n_stream * p.n_cand * 2;
+  if (wid >= total_rows) return;
+  const int kv = (int)(wid & 1);
+  long long x = wid >> 1;
+  const int c = (int)(x % p.n_cand);
+  const long long bh = x / p.n_cand;
+  int i;
+  if (c < p.n_sink_new)
+    i = c;
+  else
+    i = p.tail_start + (c - p.n_sink_new);
+  if (i >= p.q_len) return;
+  const long long pos = p.total + i;
+  int slot;
+  if (pos < p.sink)
+    slot = (int)pos;
+  else
+    slot = p.sink + (int)((pos - p.sink) % p.recent);
+  const long long src = bh * p.ring_slots + p.W + i;
+  const long long dst = bh * p.ring_slots + slot;
+  uint8_t* base = kv ? p.ring_v : p.ring_k;
+  if (p.row_bytes == 256) {
+    const uint2 v = *reinterpret_cast<const uint2*>(base + src * 256 + lane * 8);
+    *reinterpret_cast<uint2*>(base + dst * 256 + lane * 8) = v;
+  } else {
+    const uint16_t v = *reinterpret_cast<const uint16_t*>(base + src * 64 + lane * 2);
+    *reinterpret_cast<uint16_t*>(base + dst * 64 + lane * 2) = v;
+    if (lane == 0) {
+      __half* sc = kv ? p.rvs : p.rks;
+      __half* zp = kv ? p.rvz : p.rkz;
+      sc[dst] = sc[src];
+      zp[dst] = zp[src];
+    }
+  }
+}
+
+int launch_stream_commit(const duo_layer* L, const duo_cache_state* st, int q_len, cudaStream_t stream) {
+  const duo_layer_desc& d = L->d;
+  if (d.n_stream == 0 || q_len == 0) return DUO_OK;
+  CommitParams p{};
+  p.ring_k = (uint8_t*)d.ring_k;
+  p.ring_v = (uint8_t*)d.ring_v;
+  p.rks = (__half*)d.ring_k_scale;
+  p.rkz = (__half*)d.ring_k_zero;
+  p.rvs = (__half*)d.ring_v_scale;
+  p.rvz = (__half*)d.ring_v_zero;
+  p.kv_int4 = d.kv_format == DUO_KV_INT4;
+  p.row_bytes = p.kv_int4 ? 64 : 256;
+  p.batch = d.batch;
+  p.n_stream = d.n_stream;
+  p.W = d.sink + d.recent;
+  p.ring_slots = p.W + d.stage_cap;
+  p.sink = d.sink;
+  p.recent = d.recent;
+  p.q_len = q_len;
+  p.total = st->total;
+  // chunk rows i with position total+i < sink are sinks; of the rest only the last `recent` survive
+  long long n_sink_new = d.sink - st->total;
+  if (n_sink_new < 0) n_sink_new = 0;
+  if (n_sink_new > q_len) n_sink_new = q_len;
+  int tail_start = q_len - d.recent;
+  if (tail_start < (int)n_sink_new) tail_start = (int)n_sink_new;
+  p.n_sink_new = (int)n_sink_new;
+  p.tail_start = tail_start;
+  p.n_cand = (int)n_sink_new + (q_len - tail_start);
+  if (p.n_cand <= 0) return DUO_OK;
+  const long long rows = (long long)d.batch * d.n_stream * p.n_cand * 2;
+  const long long blocks = (rows + 7) / 8;
+  stream_commit_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone INT4 quantise / dequantise (K1 / K2)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quant_int4_kernel(const __half* in, long long in_row_stride, long long rows,
+                                                         uint8_t* packed, __half* scale, __half* zero) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const Vec4<__half> xv = *reinterpret_cast<const Vec4<__half>*>(in + r * in_row_stride + lane * 4);
+  float x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = __half2float(xv.v[i]);
+  quant_row_int4(x, lane, packed + r * 64, scale + r, zero + r);
+}
+
+__global__ void __launch_bounds__(256) dequant_int4_kernel(const uint8_t* packed, const __half* scale,
+                                                           const __half* zero, long long rows, __half* out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const uint16_t two = *reinterpret_cast<const uint16_t*>(packed + r * 64 + lane * 2);
+  const __half s = scale[r], z = zero[r];
+  const uint32_t b0 = two & 0xff, b1 = two >> 8;
+  const uint32_t q[4] = {b0 >> 4, b0 & 0xf, b1 >> 4, b1 & 0xf};
+  Vec4<__half> o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o.v[i] = __hadd(__hmul(__float2half((float)q[i]), s), z);
+  *reinterpret_cast<Vec4<__half>*>(out + r * 128 + lane * 4) = o;
+}
+
+int launch_quant_int4(const void* in, long long in_row_stride, long long rows, void* packed, void* scale, void* zero,
+                      cudaStream_t stream) {
+  if (rows == 0) return DUO_OK;
+  const long long blocks = (rows + 7) / 8;
+  quant_int4_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __half*)in, in_row_stride, rows, (uint8_t*)packed,
+                                                          (__half*)scale, (__half*)zero);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+int launch_dequant_int4(const void* packed, const void* scale, const void* zero, long long rows, void* out,
+                        cudaStream_t stream) {
+  if (rows == 0) return DUO_OK;
+  const long long blocks = (rows + 7) / 8;
+  dequant_int4_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const uint8_t*)packed, (const __half*)scale,
+                                                            (const __half*)zero, rows, (__half*)out);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+}  // namespace duo

@@ -1,0 +1,298 @@
+"""Head-major DuoAttention KV cache for B200.
+
+Replaces the reference's token-major caches —
+
+* ``DuoAttentionStaticKVCache``       (duo_attn/patch/static_kv_cache.py:18-315)
+* the per-layer tuple cache           (duo_attn/patch/llama.py:168-171,292-301)
+* ``DuoAttentionStaticINT4KVCache``   (demo/int4_kv.py:115-492)
+
+— with one layout designed for coalesced 128 B HBM loads and TMA tiles:
+
+    full_k / full_v : [B, n_full,   capacity,                 128]   retrieval heads
+    ring_k / ring_v : [B, n_stream, sink + recent + stage_cap, 128]  streaming heads
+                      slots [0,sink) sinks | [sink,sink+recent) true ring | staging for the chunk in flight
+
+The streaming cache is a real ring (token ``p`` lives in slot ``sink + (p - sink) % recent``): the
+reference's per-step compaction copies (static_kv_cache.py:127-167) become index arithmetic.  The Python
+object only owns buffers and three integers per layer; all data movement and math is CUDA
+(``csrc/``) reached through the C ABI.  Public methods keep the reference's names and semantics:
+``kv_seq_len``, ``clear()``, ``evict_last(n)``, ``memory_usage``; overflow raises ``ValueError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _C
+
+
+def _count_full(row) -> int:
+    return int((np.asarray(row, dtype=np.float64) > 0.5).sum())
+
+
+# ---- ring arithmetic (pure integers; the CUDA side implements the same formulas in duo_common.cuh) ----
+def ring_slot(pos: int, sink: int, recent: int) -> int:
+    """Slot of token ``pos`` in the streaming cache: sinks map to themselves, the rest into the ring."""
+    return pos if pos < sink else sink + (pos - sink) % recent
+
+
+def ring_advance(total: int, lo: int, n: int, sink: int, recent: int):
+    """State after appending ``n`` tokens: the ring keeps the last ``recent`` positions."""
+    total += n
+    return total, max(lo, total - recent, sink)
+
+
+def ring_evict(total: int, lo: int, n: int, sink: int):
+    """State after ``evict_last(n)`` (static_kv_cache.py:290-297): the newest ``n`` tokens are dropped."""
+    total = max(0, total - n)
+    return total, max(sink, min(lo, total))
+
+
+def ring_live_positions(total: int, lo: int, sink: int):
+    """Token positions a streaming head can still see (what the reference's compacted cache holds)."""
+    return list(range(0, min(total, sink))) + list(range(max(lo, sink), total))
+
+
+class DuoKVCache:
+    def __init__(
+        self,
+        num_layers: int,
+        num_heads: int,
+        num_kv_heads: int,
+        head_dim: int,
+        num_full_kv_head_list: Sequence[int],
+        batch_size: int,
+        max_size: int,
+        sink_size: int,
+        recent_size: int,
+        dtype: torch.dtype,
+        device,
+        stage_cap: int = 64,
+        kv_format: str = "same",
+        growable: bool = False,
+    ):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("DuoKVCache lives in GPU memory: the B200 kernels have no CPU fallback")
+        if head_dim != 128:
+            raise ValueError(f"head_dim {head_dim} not supported (the kernels are specialised for 128)")
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError(f"dtype {dtype} not supported (bf16 / fp16)")
+        if kv_format not in ("same", "int4"):
+            raise ValueError(f"kv_format {kv_format!r} not supported")
+        if kv_format == "int4" and dtype != torch.float16:
+            raise ValueError("INT4 KV requires fp16 activations (demo/run_duo_w8a8kv4.py:41-45)")
+        self.lib = _C.load()
+        self.batch_size, self.max_size = int(batch_size), int(max_size)
+        self.sink_size, self.recent_size = int(sink_size), int(recent_size)
+        self.num_layers, self.num_heads, self.num_kv_heads = num_layers, num_heads, num_kv_heads
+        self.num_kv_groups = num_heads // num_kv_heads
+        self.head_dim = head_dim
+        self.dtype, self.device = dtype, device
+        self.kv_format = kv_format
+        self.growable = growable
+        self.num_full_kv_head_list = [int(n) for n in num_full_kv_head_list]
+        self.num_streaming_kv_head_list = [num_kv_heads - n for n in self.num_full_kv_head_list]
+        assert len(self.num_full_kv_head_list) == num_layers
+        # occupancy, per layer (mirrors kv_seq_len_list / streaming_kv_seq_len_list of the reference)
+        self.kv_seq_len_list = [0] * num_layers   # retrieval cache length
+        self.total_list = [0] * num_layers        # tokens seen by the streaming heads
+        self.lo_list = [self.sink_size] * num_layers
+        self.full_cap_list = [self.max_size] * num_layers
+        self.stage_cap_list = [max(1, int(stage_cap))] * num_layers
+        self.tensors: List[dict] = []
+        self.handles: List[Optional[int]] = [None] * num_layers
+        for l in range(num_layers):
+            self.tensors.append(self._alloc_layer(l, self.full_cap_list[l], self.stage_cap_list[l]))
+            self._make_handle(l)
+        ws = self.lib.duo_workspace_bytes(self.batch_size, num_kv_heads, self.num_kv_groups, _C.DECODE_MAX_Q)
+        self.workspace = torch.zeros(ws, dtype=torch.uint8, device=device)
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def W(self):
+        return self.sink_size + self.recent_size
+
+    def _alloc_layer(self, l, full_cap, stage_cap):
+        nf, ns = self.num_full_kv_head_list[l], self.num_streaming_kv_head_list[l]
+        B, D, dev = self.batch_size, self.head_dim, self.device
+        slots = self.W + stage_cap
+        t = {}
+        if self.kv_format == "same":
+            for name, heads, rows in (("full_k", nf, full_cap), ("full_v", nf, full_cap),
+                                      ("ring_k", ns, slots), ("ring_v", ns, slots)):
+                t[name] = torch.zeros(B, heads, rows, D, dtype=self.dtype, device=dev)
+        else:
+            for name, heads, rows in (("full_k", nf, full_cap), ("full_v", nf, full_cap),
+                                      ("ring_k", ns, slots), ("ring_v", ns, slots)):
+                t[name] = torch.zeros(B, heads, rows, D // 2, dtype=torch.uint8, device=dev)
+                t[name + "_scale"] = torch.zeros(B, heads, rows, dtype=torch.float16, device=dev)
+                t[name + "_zero"] = torch.zeros(B, heads, rows, dtype=torch.float16, device=dev)
+        return t
+
+    def _make_handle(self, l):
+        if self.handles[l] is not None:
+            self.lib.duo_layer_destroy(self.handles[l])
+            self.handles[l] = None
+        t = self.tensors[l]
+        d = _C.LayerDesc()
+        for name in ("full_k", "full_v", "ring_k", "ring_v"):
+            setattr(d, name, t[name].data_ptr() if t[name].numel() else None)
+            for suf in ("_scale", "_zero"):
+                key = name + suf
+                setattr(d, key, t[key].data_ptr() if key in t and t[key].numel() else None)
+        d.full_cap = self.full_cap_list[l]
+        d.batch = self.batch_size
+        d.n_full = self.num_full_kv_head_list[l]
+        d.n_stream = self.num_streaming_kv_head_list[l]
+        d.group = self.num_kv_groups
+        d.head_dim = self.head_dim
+        d.sink, d.recent = self.sink_size, self.recent_size
+        d.stage_cap = self.stage_cap_list[l]
+        d.dtype = _C.DT_BF16 if self.dtype == torch.bfloat16 else _C.DT_FP16
+        d.kv_format = _C.KV_SAME if self.kv_format == "same" else _C.KV_INT4
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _C.check(self.lib.duo_layer_create(C.byref(d), C.byref(h)))
+        self.handles[l] = h.value
+
+    def __del__(self):
+        try:
+            for h in self.handles:
+                if h is not None:
+                    self.lib.duo_layer_destroy(h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _ensure_room(self, l, q_len):
+        """Grow the staging area (always allowed) and, for growable caches (tuple-path compatibility,
+        where the reference simply torch.cat's), the retrieval cache."""
+        need_full = self.kv_seq_len_list[l] + q_len
+        grow_full = need_full > self.full_cap_list[l]
+        if grow_full and not self.growable:
+            # same check and message as static_kv_cache.py:112-115
+            raise ValueError(
+                f"Trying to put {q_len} KVs into a cache with max size {self.full_cap_list[l]}, "
+                f"current size: {self.kv_seq_len_list[l]}."
+            )
+        grow_stage = q_len > self.stage_cap_list[l]
+        if not (grow_full or grow_stage):
+            return
+        new_full = self.full_cap_list[l]
+        if need_full > new_full:
+            new_full = max(need_full, 2 * new_full, 256)
+        new_stage = max(self.stage_cap_list[l], q_len)
+        old = self.tensors[l]
+        new = self._alloc_layer(l, new_full, new_stage)
+        n = self.kv_seq_len_list[l]
+        for name, t in old.items():
+            if name.startswith("full"):
+                new[name][:, :, :n].copy_(t[:, :, :n])
+            else:
+                new[name][:, :, : self.W].copy_(t[:, :, : self.W])
+        self.tensors[l] = new
+        self.full_cap_list[l] = new_full
+        self.stage_cap_list[l] = new_stage
+        self._make_handle(l)
+
+    def state(self, l) -> _C.CacheState:
+        return _C.CacheState(self.kv_seq_len_list[l], self.total_list[l], self.lo_list[l])
+
+    def advance(self, l, q_len):
+        self.kv_seq_len_list[l] += q_len
+        self.total_list[l], self.lo_list[l] = ring_advance(self.total_list[l], self.lo_list[l], q_len,
+                                                           self.sink_size, self.recent_size)
+
+    # ------------------------------------------------------------------------------------------
+    # reference-compatible surface (static_kv_cache.py:100-107, 285-315)
+    @property
+    def kv_seq_len(self):
+        return self.kv_seq_len_list[-1]
+
+    @property
+    def streaming_kv_seq_len(self):
+        """Rows the reference's compacted streaming cache would hold (sinks + live ring entries)."""
+        tot, lo = self.total_list[-1], self.lo_list[-1]
+        return min(tot, self.sink_size) + max(0, tot - max(lo, self.sink_size))
+
+    def clear(self):
+        for l in range(self.num_layers):
+            self.kv_seq_len_list[l] = 0
+            self.total_list[l] = 0
+            self.lo_list[l] = self.sink_size
+
+    def evict_last(self, num_tokens):
+        for l in range(self.num_layers):
+            self.kv_seq_len_list[l] = max(0, self.kv_seq_len_list[l] - num_tokens)
+            self.total_list[l], self.lo_list[l] = ring_evict(self.total_list[l], self.lo_list[l], num_tokens,
+                                                             self.sink_size)
+
+    @property
+    def memory_usage(self):
+        tot = 0
+        for t in self.tensors:
+            for v in t.values():
+                tot += v.element_size() * v.numel()
+        return tot
+
+    # ------------------------------------------------------------------------------------------
+    def attend(self, l, qkv, cos, sin, rope_mode, out, scale=None, force_mma=False):
+        """The fused per-layer hot path: RoPE + append, mixed-head attention, ring commit.
+
+        qkv  ``[B, S, (Hq + 2 Hkv) * D]`` (last dim contiguous) — q is rotated in place.
+        out  ``[B, S, Hq, D]`` contiguous, written.
+        """
+        if not qkv.is_cuda or not out.is_cuda:
+            raise RuntimeError("duo_attention_b200 kernels need CUDA tensors (no CPU fallback)")
+        B, S, width = qkv.shape
+        assert B == self.batch_size and width == (self.num_heads + 2 * self.num_kv_heads) * self.head_dim
+        assert qkv.stride(2) == 1 and qkv.stride(0) == S * qkv.stride(1), "qkv rows must be uniformly strided"
+        assert out.is_contiguous() and qkv.dtype == self.dtype and out.dtype == self.dtype
+        self._ensure_room(l, S)
+        st = self.state(l)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        h = self.handles[l]
+        lib = self.lib
+        if scale is None:
+            scale = self.head_dim ** -0.5
+        cp = cos.data_ptr() if cos is not None else None
+        sp = sin.data_ptr() if sin is not None else None
+        _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode, S, stream))
+        fn = lib.duo_attention_mma if force_mma else lib.duo_attention
+        _C.check(fn(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), S, float(scale),
+                    self.workspace.data_ptr(), self.workspace.numel(), stream))
+        _C.check(lib.duo_stream_commit(h, C.byref(st), S, stream))
+        self.advance(l, S)
+        return out
+
+
+class DuoAttentionStaticKVCache(DuoKVCache):
+    """Drop-in for the reference class of the same name (static_kv_cache.py:18-98): same constructor
+    arguments (plus optional keyword extras), same ``clear`` / ``evict_last`` / ``memory_usage`` /
+    ``kv_seq_len`` surface, head-major storage underneath."""
+
+    def __init__(self, model, full_attention_heads, batch_size, max_size, sink_size, recent_size,
+                 prefilling_chunk_size: int = 64, kv_format: str = "same"):
+        p = next(model.parameters())
+        cfg = model.config
+        head_dim = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+        super().__init__(
+            num_layers=cfg.num_hidden_layers,
+            num_heads=cfg.num_attention_heads,
+            num_kv_heads=cfg.num_key_value_heads,
+            head_dim=head_dim,
+            num_full_kv_head_list=[_count_full(r) for r in full_attention_heads],
+            batch_size=batch_size,
+            max_size=max_size,
+            sink_size=sink_size,
+            recent_size=recent_size,
+            dtype=p.dtype,
+            device=p.device,
+            stage_cap=prefilling_chunk_size,
+            kv_format=kv_format,
+            growable=False,
+        )

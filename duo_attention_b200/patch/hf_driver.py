@@ -1,0 +1,153 @@
+"""Model / decoder-layer / attention forwards that route HuggingFace Llama & Mistral through the
+B200 kernels.
+
+The reference swaps ``.forward`` on ForCausalLM / Model / DecoderLayer / Attention with HF-4.34-style
+functions (duo_attn/patch/tuple_kv_cache.py:241-490, static_kv_cache.py:318-567) and an attention
+forward that calls FlashAttention-2 twice (llama.py:146-306, :309-434).  Here the causal-LM forward is
+replaced by one driver written against attributes that are stable across transformers versions (the
+``nn.Linear`` projections, norms, ``embed_tokens``, ``lm_head``, ``rotary_emb``), and each layer's
+attention is ONE call into ``DuoKVCache.attend`` (RoPE+append → fused mixed-head attention → ring
+commit, all CUDA).  Call protocol is the reference's:
+
+    out = model(input_ids=ids, past_key_values=None | cache, use_cache=True)
+    out.logits[:, -1, :]          # only the last position is produced
+    out.past_key_values           # feed back verbatim (a DuoKVCache here, a tuple in the reference)
+"""
+from __future__ import annotations
+
+import types
+from typing import Optional
+
+import torch
+from transformers.modeling_outputs import CausalLMOutputWithPast
+
+from .. import _C
+from ..kv_cache import DuoKVCache
+
+
+class _AttnPlan:
+    """Per-attention-module state created at enable time."""
+
+    def __init__(self, n_full, n_kv, group, head_dim):
+        self.n_full, self.n_kv, self.group, self.head_dim = n_full, n_kv, group, head_dim
+        self.wqkv = None
+        self.bqkv = None
+
+
+def _fuse_qkv(attn):
+    """Concatenate the (already reordered) q/k/v projections into one GEMM operand on first use and
+    re-point the three nn.Linear weights at views of it (no extra memory)."""
+    plan = attn._duo_plan
+    w = torch.cat([attn.q_proj.weight.data, attn.k_proj.weight.data, attn.v_proj.weight.data], dim=0).contiguous()
+    nq, nk = attn.q_proj.weight.shape[0], attn.k_proj.weight.shape[0]
+    attn.q_proj.weight.data = w[:nq]
+    attn.k_proj.weight.data = w[nq : nq + nk]
+    attn.v_proj.weight.data = w[nq + nk :]
+    plan.wqkv = w
+    if attn.q_proj.bias is not None:
+        plan.bqkv = torch.cat([attn.q_proj.bias.data, attn.k_proj.bias.data, attn.v_proj.bias.data]).contiguous()
+
+
+def duo_attention_layer_forward(attn, hidden_states, cos, sin, kv_cache: DuoKVCache, layer_idx: int,
+                                rope_mode: int = _C.ROPE_HF):
+    """The hot path of one layer (replaces llama.py:146-306 / :309-434)."""
+    plan = attn._duo_plan
+    if plan.wqkv is None or plan.wqkv.device != hidden_states.device:
+        _fuse_qkv(attn)
+    B, S, _ = hidden_states.shape
+    qkv = torch.nn.functional.linear(hidden_states, plan.wqkv, plan.bqkv)
+    out = torch.empty(B, S, plan.n_kv * plan.group, plan.head_dim, dtype=qkv.dtype, device=qkv.device)
+    kv_cache.attend(layer_idx, qkv, cos, sin, rope_mode, out)
+    return attn.o_proj(out.view(B, S, -1))
+
+
+def _new_dynamic_cache(model, batch_size, first_len):
+    plans = [layer.self_attn._duo_plan for layer in model.model.layers]
+    p = next(model.parameters())
+    cfg = model.config
+    return DuoKVCache(
+        num_layers=len(plans),
+        num_heads=cfg.num_attention_heads,
+        num_kv_heads=cfg.num_key_value_heads,
+        head_dim=plans[0].head_dim,
+        num_full_kv_head_list=[pl.n_full for pl in plans],
+        batch_size=batch_size,
+        max_size=max(256, 2 * first_len),
+        sink_size=model._duo_sink,
+        recent_size=model._duo_recent,
+        dtype=p.dtype,
+        device=p.device,
+        stage_cap=first_len,
+        growable=True,
+    )
+
+
+def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, attention_mask=None,
+                          position_ids=None, past_key_values=None, inputs_embeds=None, labels=None,
+                          use_cache=None, **kwargs):
+    """Patched ``ForCausalLM.forward``.  ``past_key_values`` is ``None`` (first call: a growable
+    DuoKVCache is created, tuple-path behaviour) or a ``DuoKVCache`` / ``DuoAttentionStaticKVCache``
+    (static-path behaviour, benchmark_static.py:58-103).  Padding is not supported, exactly like the
+    reference's duo forwards (llama.py:154)."""
+    if labels is not None:
+        raise ValueError("the DuoAttention eval forward does not compute a loss")
+    base = self.model
+    if inputs_embeds is None:
+        inputs_embeds = base.embed_tokens(input_ids)
+    B, S, _ = inputs_embeds.shape
+    cache = past_key_values
+    if cache is None:
+        cache = _new_dynamic_cache(self, B, S)
+    elif not isinstance(cache, DuoKVCache):
+        raise ValueError("past_key_values must be None or a DuoKVCache produced by this model")
+    past_len = cache.kv_seq_len
+    if position_ids is None:
+        position_ids = torch.arange(past_len, past_len + S, dtype=torch.long, device=inputs_embeds.device)[None]
+    else:
+        position_ids = position_ids.view(-1, S).long()[:1]
+    cos, sin = base.rotary_emb(inputs_embeds, position_ids)  # [1, S, D] in the activation dtype
+    cos, sin = cos[0].contiguous(), sin[0].contiguous()
+    h = inputs_embeds
+    for idx, layer in enumerate(base.layers):
+        res = h
+        x = layer.input_layernorm(h)
+        x = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
+        h = res + x
+        res = h
+        x = layer.post_attention_layernorm(h)
+        x = layer.mlp(x)
+        h = res + x
+    h = base.norm(h[:, -1:, :])
+    logits = self.lm_head(h)
+    if getattr(self, "_duo_logits_float", True):
+        logits = logits.float()
+    return CausalLMOutputWithPast(logits=logits, past_key_values=cache if use_cache is not False else None)
+
+
+def install(model, full_attention_heads, sink_size, recent_size, logits_float=True):
+    """Shared body of enable_{llama,mistral}_duo_attention_eval (llama.py:504-554): reorder weights so
+    retrieval heads come first, remember the split, swap the model forward."""
+    from .reorder import reorder_linear_weights, reorder_full_attn_heads
+
+    cfg = model.config
+    n_heads, n_kv = cfg.num_attention_heads, cfg.num_key_value_heads
+    head_dim = getattr(cfg, "head_dim", None) or cfg.hidden_size // n_heads
+    group = n_heads // n_kv
+    p = next(model.parameters())
+    for idx, layer in enumerate(model.model.layers):
+        module = layer.self_attn
+        gate = torch.tensor(full_attention_heads[idx], device=p.device, dtype=p.dtype)
+        reorder_linear_weights(module.q_proj, gate, group * head_dim, "out")
+        reorder_linear_weights(module.k_proj, gate, head_dim, "out")
+        reorder_linear_weights(module.v_proj, gate, head_dim, "out")
+        reorder_linear_weights(module.o_proj, gate, group * head_dim, "in")
+        gate = reorder_full_attn_heads(gate)
+        module.sink_size = sink_size
+        module.recent_size = recent_size
+        module.register_buffer("full_attention_heads", gate)
+        module._duo_plan = _AttnPlan(int((gate > 0.5).sum().item()), n_kv, group, head_dim)
+    model._duo_sink = sink_size
+    model._duo_recent = recent_size
+    model._duo_logits_float = logits_float
+    model.forward = types.MethodType(duo_causal_lm_forward, model)
+    return model

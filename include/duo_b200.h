@@ -1,0 +1,187 @@
+/*
+ * duo_b200.h — C ABI of libduo_b200.so: DuoAttention's mixed-head (retrieval + streaming)
+ * attention hot path, hand-written for NVIDIA B200 (sm_100a).
+ *
+ * Plain C: raw device pointers, integers and a cudaStream_t passed as void*.  No torch types.
+ * Every function returns 0 on success or a negative DUO_E* code; the message of the last error
+ * on the calling thread is available from duo_last_error_string().  No function throws,
+ * none allocates device memory (the caller — PyTorch in the reference — owns all buffers),
+ * and all work is enqueued on the given stream (re-entrant per stream).
+ *
+ * What each entry point replaces in the reference (paths relative to mit-han-lab/duo-attention):
+ *
+ *   duo_layer_create/destroy  – the per-layer views of DuoAttentionStaticKVCache
+ *                               (duo_attn/patch/static_kv_cache.py:60-94) re-laid out head-major;
+ *                               also pre-encodes the TMA descriptors of the four cache tensors.
+ *   duo_rope_append           – apply_rotary_pos_emb (duo_attn/patch/llama.py:177-184) or
+ *                               apply_rope_inplace (duo_attn/patch/flashinfer_utils.py:29-59),
+ *                               kv_cache.split_kv + put_full_kv (static_kv_cache.py:252-263,109-125)
+ *                               and the torch.cat of cached+new streaming KV (llama.py:385-390);
+ *                               for INT4 caches also quantize_int4_with_zero_point_per_group
+ *                               (demo/quantize_int4.cu:73-178 via demo/int4_kv.py:261-371).
+ *   duo_attention             – the flash_attn_func call pair + torch.cat
+ *                               (llama.py:225-267 / :364-421; demo/w8a8kv4_llama.py:229-274),
+ *                               both head classes in ONE launch; for INT4 caches the
+ *                               dequantize pass (demo/int4_kv.py:373-436) is folded into the K/V load.
+ *   duo_stream_commit         – compress_and_replace_streaming_kv (static_kv_cache.py:127-167,
+ *                               llama.py:273-290; demo/int4_kv.py:438-492) as a ring advance.
+ *   duo_quant_int4 / duo_dequant_int4 – the two kernels of demo/quantize_int4.cu (K1 :73-144,
+ *                               K2 :9-42) as stand-alone ops (K2 is test/diagnostic only: the
+ *                               product never materialises a dequantised cache).
+ */
+#ifndef DUO_B200_H
+#define DUO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DUO_API __attribute__((visibility("default")))
+#else
+#define DUO_API
+#endif
+
+#define DUO_OK 0
+#define DUO_EINVAL -1     /* bad argument / unsupported shape          */
+#define DUO_EOVERFLOW -2  /* KV cache capacity exceeded (ValueError in the reference,
+                             static_kv_cache.py:112-115)               */
+#define DUO_ECUDA -3      /* CUDA runtime / driver error                */
+#define DUO_EWORKSPACE -4 /* workspace too small                        */
+
+/* element type of activations and (for DUO_KV_SAME) of the KV cache */
+#define DUO_DT_BF16 0
+#define DUO_DT_FP16 1
+/* KV cache storage */
+#define DUO_KV_SAME 0 /* same dtype as activations                                     */
+#define DUO_KV_INT4 1 /* packed u4 + fp16 scale/zero per (token, head); activations fp16 */
+
+/* RoPE flavour of duo_rope_append */
+#define DUO_ROPE_NONE 0  /* q/k already rotated                                              */
+#define DUO_ROPE_HF 1    /* cos/sin tables in the activation dtype, HF op order (llama.py:177-184):
+                            round(round(x*cos) + round(rotate_half(x)*sin)) — bit-exact with torch */
+#define DUO_ROPE_FP32 2  /* cos/sin tables in fp32, fp32 math, one rounding (flashinfer semantics,
+                            flashinfer_utils.py:29-59, with accurate trig)                  */
+
+/*
+ * Geometry + buffers of ONE decoder layer's KV cache, head-major ("heads first, then tokens"):
+ *
+ *   full_k/full_v : [batch][n_full  ][full_cap            ][head_dim]   retrieval heads
+ *   ring_k/ring_v : [batch][n_stream][sink+recent+stage_cap][head_dim]  streaming heads:
+ *                   slots [0,sink) = attention sinks, [sink,sink+recent) = ring of the most recent
+ *                   tokens (token p lives in slot sink + (p-sink) % recent), and
+ *                   [sink+recent, +stage_cap) = staging area holding the K/V of the chunk being
+ *                   processed until duo_stream_commit moves its tail into the ring.
+ *   KV heads are in the reference's reordered order: retrieval heads first
+ *   (duo_attn/patch/utils.py:6-45); q-head i reads kv-head i / group.
+ *
+ *   DUO_KV_INT4: the k/v tensors hold head_dim/2 bytes per row (high nibble = even element,
+ *   demo/quantize_int4.cu:33-40,137) and *_scale / *_zero are fp16 [batch][heads][slots]
+ *   (group_size == head_dim == 128, demo/int4_kv.py:140).
+ */
+typedef struct duo_layer_desc {
+  void* full_k;
+  void* full_v;
+  void* ring_k;
+  void* ring_v;
+  void* full_k_scale; /* INT4 only, else NULL */
+  void* full_k_zero;
+  void* full_v_scale;
+  void* full_v_zero;
+  void* ring_k_scale;
+  void* ring_k_zero;
+  void* ring_v_scale;
+  void* ring_v_zero;
+  int64_t full_cap;  /* token capacity of the retrieval cache          */
+  int32_t batch;
+  int32_t n_full;    /* retrieval KV heads in this layer (0..n_kv)      */
+  int32_t n_stream;  /* streaming KV heads (n_kv - n_full)              */
+  int32_t group;     /* q heads per kv head                             */
+  int32_t head_dim;  /* must be 128                                     */
+  int32_t sink;
+  int32_t recent;
+  int32_t stage_cap; /* max tokens per call (prefill chunk capacity)    */
+  int32_t dtype;     /* DUO_DT_*                                        */
+  int32_t kv_format; /* DUO_KV_*                                        */
+} duo_layer_desc;
+
+/* Streaming/retrieval cache occupancy BEFORE the call (host integers; the caller advances them,
+ * exactly like kv_seq_len_list / streaming_kv_seq_len_list in static_kv_cache.py:44-45).
+ *   full_len : tokens in the retrieval cache
+ *   total    : tokens seen so far by the streaming heads (== full_len unless evict_last ran)
+ *   lo       : oldest token position still valid in the ring (>= sink); ring content is
+ *              positions [lo, total) ∩ [sink, ∞), sinks are positions [0, min(total, sink)).   */
+typedef struct duo_cache_state {
+  int64_t full_len;
+  int64_t total;
+  int64_t lo;
+} duo_cache_state;
+
+typedef struct duo_layer duo_layer; /* opaque: desc + pre-encoded TMA descriptors (host memory) */
+
+DUO_API int duo_layer_create(const duo_layer_desc* desc, duo_layer** out);
+DUO_API void duo_layer_destroy(duo_layer* layer);
+
+/* Bytes of scratch duo_attention needs for this geometry (split-KV partials + arrival counters).
+ * The buffer must be zero-initialised once; the kernels leave the counters zeroed.            */
+DUO_API size_t duo_workspace_bytes(int32_t batch, int32_t n_kv_heads, int32_t group, int32_t max_q_len);
+
+/*
+ * RoPE + KV append for one chunk of q_len tokens (all batch rows).
+ *   qkv       : [batch][q_len][(n_q + 2 n_kv) * head_dim] fused projection output, row stride
+ *               qkv_row_stride elements; q is rotated IN PLACE, k is rotated on its way into the
+ *               caches, v is copied (INT4: both quantised, K1 semantics).
+ *   cos, sin  : [q_len][head_dim] tables (dtype per rope_mode), shared by all batch rows.
+ * Retrieval heads' K/V go to full_{k,v}[.., full_len + t, :]; streaming heads' K/V go to the
+ * staging slots ring_{k,v}[.., sink+recent + t, :].
+ * Returns DUO_EOVERFLOW if full_len + q_len > full_cap or q_len > stage_cap.
+ */
+DUO_API int duo_rope_append(const duo_layer* layer, const duo_cache_state* st, void* qkv, int64_t qkv_row_stride,
+                    const void* cos, const void* sin, int32_t rope_mode, int32_t q_len, void* stream);
+
+/*
+ * Mixed-head attention for one chunk, both head classes in one launch.  Must follow
+ * duo_rope_append for the same chunk and state.
+ *   q   : [batch][q_len][n_q][head_dim], token stride q_row_stride elements (the rotated q inside qkv)
+ *   out : [batch][q_len][n_q][head_dim] contiguous
+ * Retrieval q-heads attend keys [0, full_len + t] (bottom-right causal); streaming q-heads attend
+ * the valid sink+ring slots plus staged chunk tokens [0, t].  softmax scale `scale`
+ * (1/sqrt(head_dim) in the reference), fp32 softmax, P rounded to the activation dtype before PV.
+ * q_len <= DUO_DECODE_MAX_Q uses the split-KV bandwidth kernel, larger chunks the tensor-core
+ * prefill kernel.
+ */
+#define DUO_DECODE_MAX_Q 16
+DUO_API int duo_attention(const duo_layer* layer, const duo_cache_state* st, const void* q, int64_t q_row_stride,
+                  void* out, int32_t q_len, float scale, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Diagnostic twin of duo_attention that always takes the mma.sync (bandwidth) kernel family, also for
+ * chunk shapes duo_attention hands to the tcgen05 prefill kernel.  16-bit KV only.  Used by the parity
+ * tests to cross-check the two kernel families against each other. */
+DUO_API int duo_attention_mma(const duo_layer* layer, const duo_cache_state* st, const void* q, int64_t q_row_stride,
+                              void* out, int32_t q_len, float scale, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
+/* Move the tail of the staged chunk into sink/ring slots (call after duo_attention). */
+DUO_API int duo_stream_commit(const duo_layer* layer, const duo_cache_state* st, int32_t q_len, void* stream);
+
+/*
+ * Stand-alone INT4 group quantisation, group_size == 128 == row length.
+ *   in    : fp16 rows, row r at in + r*in_row_stride (elements)
+ *   packed: [rows][64] u8, scale/zero: fp16 [rows]
+ */
+DUO_API int duo_quant_int4(const void* in, int64_t in_row_stride, int64_t rows, void* packed, void* scale,
+                   void* zero, void* stream);
+DUO_API int duo_dequant_int4(const void* packed, const void* scale, const void* zero, int64_t rows, void* out,
+                     void* stream);
+
+DUO_API const char* duo_last_error_string(void);
+DUO_API int duo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUO_B200_H */

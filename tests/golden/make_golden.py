@@ -1,0 +1,186 @@
+"""Generate the golden fixtures in this directory by running the REFERENCE's own code.
+
+Run in the build container (needs /root/reference; the fixtures are committed so the tests never
+need it):
+
+    python tests/golden/make_golden.py
+
+How the reference is made importable here (SURVEY.md §8c says it is not, as-is):
+  * transformers 5.5 no longer re-exports ``List / Union / CrossEntropyLoss`` from modeling_llama — we add
+    those three names to the real module before importing ``duo_attn.patch.llama``;
+  * ``tensor_parallel``, ``accelerate``, ``matplotlib`` (absent, unused by the eval forward) are stubbed
+    with empty modules;
+  * the two CUDA-only third-party calls are swapped for the contract restatements in
+    ``oracle/duo_oracle.py``: ``flash_attn_func`` -> ``flash_attn_contract`` and flashinfer's
+    ``apply_rope_inplace`` -> ``rope_flashinfer`` (written back in place).
+Everything else that runs is the reference's code, unmodified: ``llama_duo_attention_forward_one_way_
+reordered`` (llama.py:146-306), ``..._static`` (:309-434), ``DuoAttentionStaticKVCache``
+(static_kv_cache.py:18-315), ``reorder_linear_weights`` / ``reorder_full_attn_heads``
+(patch/utils.py:6-45), ``load_attn_pattern`` / ``sparsify_attention_heads`` (duo_attn/utils.py:326-373).
+
+Fixture inputs are regenerated from seeds by ``tests/golden_cases.py`` (shared with the tests); each
+fixture stores an fp64 checksum of its inputs so RNG drift is detected rather than silently accepted.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+import typing
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+REF = "/root/reference"
+
+
+def import_reference():
+    import transformers.models.llama.modeling_llama as ml
+    import transformers.models.mistral.modeling_mistral as mm
+    from torch.nn import CrossEntropyLoss
+
+    for m in (ml, mm):
+        for n, v in dict(List=typing.List, Union=typing.Union, CrossEntropyLoss=CrossEntropyLoss).items():
+            if not hasattr(m, n):
+                setattr(m, n, v)
+    class _Anything(types.ModuleType):
+        """Stub module: any attribute is a dummy callable (only import-time names are touched)."""
+
+        def __getattr__(self, item):
+            if item.startswith("__"):
+                raise AttributeError(item)
+            return lambda *a, **k: None
+
+    for name in ("tensor_parallel", "tensor_parallel.pretrained_model", "tensor_parallel.config",
+                 "tensor_parallel.communications", "tensor_parallel.aux_actions", "tensor_parallel.state_actions",
+                 "tensor_parallel.autoconfig", "accelerate", "accelerate.utils", "matplotlib",
+                 "matplotlib.pyplot", "matplotlib.colors", "seaborn"):
+        if name not in sys.modules:
+            m = _Anything(name)
+            m.__path__ = []  # let `import a.b` treat it as a package
+            sys.modules[name] = m
+    sys.modules["tensor_parallel.pretrained_model"].TensorParallelPreTrainedModel = type("TPM", (), {})
+    # put the reference FIRST so `import duo_attn` resolves to it, not to this repo's shim
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == "duo_attn" or k.startswith("duo_attn.")]:
+        del sys.modules[k]
+    import duo_attn.patch.llama as ref_llama
+    import duo_attn.patch.utils as ref_putils
+
+    try:
+        import duo_attn.utils as ref_utils
+    except Exception as e:  # pragma: no cover - only if more stubs are needed
+        print("duo_attn.utils import failed:", repr(e))
+        ref_utils = None
+    return ref_llama, ref_putils, ref_utils
+
+
+def main():
+    from oracle import duo_oracle as O
+    import golden_cases as GC
+
+    ref_llama, ref_putils, ref_utils = import_reference()
+    assert ref_llama.__file__.startswith(REF), ref_llama.__file__
+
+    # swap the CUDA-only third-party calls for the contract restatements
+    ref_llama.flash_attn_func = O.flash_attn_contract
+
+    def rope_inplace(q, k, offsets, rope_scale, rope_theta, indptr=None):
+        q2, k2 = O.rope_flashinfer(q, k, int(offsets.reshape(-1)[0]), rope_scale, rope_theta)
+        q.copy_(q2)
+        k.copy_(k2)
+        return q, k
+
+    ref_llama.apply_rope_inplace = rope_inplace
+
+    # ---------------------------------------------------------------- attention-layer fixtures
+    for case in GC.LAYER_CASES:
+        name = case["name"]
+        data = GC.make_layer_inputs(case)
+        mod = GC.RefAttnModule(case, data, ref_putils)  # reference reorder functions run inside
+        outs = []
+        if case["path"] == "tuple":
+            past = None
+            pos = 0
+            for hs in data["chunks"]:
+                S = hs.shape[1]
+                position_ids = torch.arange(pos, pos + S)[None]
+                out, _, past = ref_llama.llama_duo_attention_forward_one_way_reordered(
+                    mod, hs, position_ids=position_ids, past_key_value=past, use_cache=True)
+                outs.append(out)
+                pos += S
+            extra = dict(final_full_len=past[0].shape[2], final_stream_len=past[1].shape[2])
+        else:
+            fake_model = GC.FakeModel(case, mod)
+            cache = ref_llama.DuoAttentionStaticKVCache(
+                fake_model, [data["gate"].numpy()], data["B"], case["max_size"], case["sink"], case["recent"])
+            pos = 0
+            for i, hs in enumerate(data["chunks"]):
+                S = hs.shape[1]
+                position_ids = torch.arange(pos, pos + S)[None]
+                out, _ = ref_llama.llama_duo_attention_forward_one_way_reordered_static(
+                    mod, hs, position_ids=position_ids, kv_cache=cache, layer_idx=0)
+                outs.append(out)
+                pos += S
+                ev = case.get("evict_after", {}).get(i, 0)
+                if ev:
+                    cache.evict_last(ev)
+                    pos -= ev
+            extra = dict(final_full_len=cache.kv_seq_len, final_stream_len=cache.streaming_kv_seq_len)
+        np.savez_compressed(
+            os.path.join(HERE, f"layer_{name}.npz"),
+            out=torch.cat(outs, dim=1).numpy().astype(np.float32),
+            checksum=np.float64(GC.checksum(data)),
+            **{k: np.int64(v) for k, v in extra.items()},
+        )
+        print("wrote layer", name, "tokens", sum(c.shape[1] for c in data["chunks"]), extra)
+
+    # ---------------------------------------------------------------- reorder fixtures
+    for case in GC.REORDER_CASES:
+        torch.manual_seed(case["seed"])
+        lin = torch.nn.Linear(case["in"], case["out"], bias=case["bias"])
+        gate = torch.tensor(case["gate"], dtype=torch.float32)
+        w0 = lin.weight.data.clone()
+        b0 = None if lin.bias is None else lin.bias.data.clone()
+        ref_putils.reorder_linear_weights(lin, gate, case["repeat"], case["channel"])
+        g2 = ref_putils.reorder_full_attn_heads(gate.clone())
+        np.savez_compressed(
+            os.path.join(HERE, f"reorder_{case['name']}.npz"),
+            w_in=w0.numpy(), w_out=lin.weight.data.numpy(),
+            b_in=np.zeros(0) if b0 is None else b0.numpy(),
+            b_out=np.zeros(0) if lin.bias is None else lin.bias.data.numpy(),
+            gate_out=g2.numpy(),
+        )
+        print("wrote reorder", case["name"])
+
+    # ---------------------------------------------------------------- pattern fixtures
+    if ref_utils is not None:
+        res = {}
+        pat_root = os.path.join(REF, "attn_patterns")
+        for model in sorted(os.listdir(pat_root)):
+            run = sorted(os.listdir(os.path.join(pat_root, model)))[0]
+            d = os.path.join(pat_root, model, run)
+            for sparsity in (0.0, 0.25, 0.5, 0.75, 1.0):
+                h, sink, recent = ref_utils.load_attn_pattern(d)
+                np.random.seed(42)
+                mask, true_sp = ref_utils.sparsify_attention_heads(h, None, sparsity)
+                res[f"{model}|{sparsity}"] = dict(
+                    dir=os.path.join("attn_patterns", model, run), sink=sink, recent=recent,
+                    shape=list(mask.shape), per_layer_full=mask.sum(1).astype(int).tolist(),
+                    mask_rows=["".join(str(int(v)) for v in row) for row in mask], true_sparsity=float(true_sp),
+                    clipped_sum=float(np.clip(np.loadtxt(os.path.join(d, "full_attention_heads.tsv")), 0, 1).sum()),
+                )
+        with open(os.path.join(HERE, "patterns.json"), "w") as f:
+            json.dump(res, f, indent=1, sort_keys=True)
+        print("wrote patterns", len(res))
+
+
+if __name__ == "__main__":
+    with torch.no_grad():
+        main()

@@ -1,0 +1,126 @@
+"""Case definitions + deterministic input generation shared by ``tests/golden/make_golden.py`` (which
+runs the reference on them) and the tests (which run the oracle / the CUDA kernels on them)."""
+from __future__ import annotations
+
+import types
+
+import numpy as np
+import torch
+
+D = 128  # the kernels are specialised for head_dim 128 (all four BASELINE models)
+
+LAYER_CASES = [
+    dict(name="tuple_g2_mix", path="tuple", Hq=8, Hkv=4, gate=[1, 0, 1, 0], sink=4, recent=8, hidden=64,
+         chunks=[5, 1, 1, 7, 20, 1, 1, 1, 30, 3], B=1, seed=11, theta=10000.0),
+    dict(name="tuple_g4_deploy", path="tuple", Hq=8, Hkv=2, gate=[0, 1], sink=64, recent=256, hidden=64,
+         chunks=[100, 300, 1, 1, 50, 1], B=1, seed=12, theta=500000.0),
+    dict(name="tuple_mha_allstream", path="tuple", Hq=4, Hkv=4, gate=[0, 0, 0, 0], sink=2, recent=3, hidden=32,
+         chunks=[1, 1, 1, 1, 1, 1, 1, 9, 1, 2], B=1, seed=13, theta=10000.0),
+    dict(name="tuple_g4_allfull", path="tuple", Hq=8, Hkv=2, gate=[1, 1], sink=4, recent=4, hidden=32,
+         chunks=[33, 1, 2, 1], B=1, seed=14, theta=10000.0),
+    dict(name="tuple_b2", path="tuple", Hq=4, Hkv=2, gate=[1, 0], sink=3, recent=5, hidden=32,
+         chunks=[6, 1, 4, 1, 1], B=2, seed=15, theta=10000.0),
+    dict(name="static_g4_evict", path="static", Hq=8, Hkv=2, gate=[1, 0], sink=16, recent=64, hidden=64,
+         chunks=[90, 40, 1, 1, 1, 17, 1], B=1, seed=21, theta=10000.0, rope_factor=None, max_size=256,
+         evict_after={2: 1, 3: 1}),
+    dict(name="static_g2_scaled", path="static", Hq=4, Hkv=2, gate=[0, 1], sink=8, recent=8, hidden=32,
+         chunks=[10, 10, 1, 1, 30, 1], B=1, seed=22, theta=10000.0, rope_factor=8.0, max_size=64),
+]
+
+REORDER_CASES = [
+    dict(name="q_out_bias", seed=1, **{"in": 24, "out": 48}, bias=True, gate=[0.9, 0.1, 0.7, 0.2], repeat=12,
+         channel="out"),
+    dict(name="o_in", seed=2, **{"in": 48, "out": 20}, bias=False, gate=[0.0, 1.0, 0.0, 1.0], repeat=12,
+         channel="in"),
+    dict(name="k_out_allfull", seed=3, **{"in": 16, "out": 32}, bias=False, gate=[1.0, 1.0], repeat=16,
+         channel="out"),
+]
+
+
+def make_layer_inputs(case):
+    g = torch.Generator().manual_seed(case["seed"])
+    Hq, Hkv, hid, B = case["Hq"], case["Hkv"], case["hidden"], case["B"]
+    s = hid ** -0.5
+    data = dict(
+        B=B,
+        wq=torch.randn(Hq * D, hid, generator=g) * s * 1.5,
+        wk=torch.randn(Hkv * D, hid, generator=g) * s * 1.5,
+        wv=torch.randn(Hkv * D, hid, generator=g) * s,
+        wo=torch.randn(hid, Hq * D, generator=g) * (Hq * D) ** -0.5,
+        gate=torch.tensor(case["gate"], dtype=torch.float32),
+        chunks=[torch.randn(B, n, hid, generator=g) for n in case["chunks"]],
+    )
+    return data
+
+
+def checksum(data):
+    tot = 0.0
+    for k in ("wq", "wk", "wv", "wo"):
+        tot += float(data[k].double().sum())
+    for c in data["chunks"]:
+        tot += float(c.double().abs().sum())
+    return tot
+
+
+def hf_rotary(case, dtype=torch.float32):
+    """The real transformers LlamaRotaryEmbedding for this case's theta (default rope type)."""
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+
+    cfg = LlamaConfig(hidden_size=case["Hq"] * D, num_attention_heads=case["Hq"],
+                      num_key_value_heads=case["Hkv"], head_dim=D, num_hidden_layers=1, intermediate_size=64,
+                      vocab_size=32, max_position_embeddings=4096, rope_theta=case["theta"])
+    try:
+        rp = dict(getattr(cfg, "rope_parameters", None) or {})
+        if rp.get("rope_theta") != case["theta"]:
+            rp.update(rope_theta=case["theta"], rope_type="default")
+            cfg.rope_parameters = rp
+    except Exception:
+        pass
+    return LlamaRotaryEmbedding(config=cfg)
+
+
+class RefAttnModule(torch.nn.Module):
+    """The attributes the reference forward reads from ``self`` (HF-4.45 LlamaAttention surface),
+    with weights reordered by the REFERENCE's own reorder functions (``putils`` =
+    duo_attn.patch.utils of the reference), as enable_llama_duo_attention_eval does (llama.py:523-554)."""
+
+    def __init__(self, case, data, putils):
+        super().__init__()
+        Hq, Hkv, hid = case["Hq"], case["Hkv"], case["hidden"]
+        self.num_heads, self.num_key_value_heads, self.head_dim = Hq, Hkv, D
+        self.num_key_value_groups = Hq // Hkv
+        self.hidden_size = Hq * D  # the forward only uses it for reshape(bsz, q_len, hidden_size)
+        self.q_proj = torch.nn.Linear(hid, Hq * D, bias=False)
+        self.k_proj = torch.nn.Linear(hid, Hkv * D, bias=False)
+        self.v_proj = torch.nn.Linear(hid, Hkv * D, bias=False)
+        self.o_proj = torch.nn.Linear(Hq * D, hid, bias=False)
+        self.q_proj.weight.data = data["wq"].clone()
+        self.k_proj.weight.data = data["wk"].clone()
+        self.v_proj.weight.data = data["wv"].clone()
+        self.o_proj.weight.data = data["wo"].clone()
+        gate = data["gate"].clone()
+        G = self.num_key_value_groups
+        putils.reorder_linear_weights(self.q_proj, gate, G * D, "out")
+        putils.reorder_linear_weights(self.k_proj, gate, D, "out")
+        putils.reorder_linear_weights(self.v_proj, gate, D, "out")
+        putils.reorder_linear_weights(self.o_proj, gate, G * D, "in")
+        self.register_buffer("full_attention_heads", putils.reorder_full_attn_heads(gate))
+        self.sink_size, self.recent_size = case["sink"], case["recent"]
+        self.rotary_emb = hf_rotary(case)
+        self.rope_theta = case["theta"]
+        rs = None if case.get("rope_factor") is None else {"factor": case["rope_factor"], "type": "linear"}
+        self.config = types.SimpleNamespace(rope_scaling=rs)
+
+
+class FakeModel:
+    """What DuoAttentionStaticKVCache.__init__ reads from ``model`` (static_kv_cache.py:33-40)."""
+
+    def __init__(self, case, mod):
+        self._mod = mod
+        self.config = types.SimpleNamespace(
+            num_hidden_layers=1, num_attention_heads=case["Hq"], num_key_value_heads=case["Hkv"],
+            hidden_size=case["Hq"] * D)
+
+    def parameters(self):
+        return self._mod.parameters()

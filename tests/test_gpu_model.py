@@ -1,0 +1,109 @@
+"""Model-level parity: random-init HF Llama / Mistral patched through the drop-in API
+(enable_duo_attention_eval) vs (a) the CPU oracle model that restates the reference driver
+(tuple_kv_cache.py:241-490 + llama.py:146-306) and (b) unpatched HF eager attention when every head is a
+retrieval head (weight-reorder invariance)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from duo_attn.patch import DuoAttentionStaticKVCache, enable_duo_attention_eval
+from duo_attn.patch import enable_llama_duo_attention_static_kv_cache_eval
+from oracle import duo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def tiny_model(kind="llama", layers=2, n_heads=4, n_kv=2, hidden=512, seed=0):
+    torch.manual_seed(seed)
+    if kind == "llama":
+        from transformers import LlamaConfig, LlamaForCausalLM as M
+
+        cfg = LlamaConfig(hidden_size=hidden, num_attention_heads=n_heads, num_key_value_heads=n_kv,
+                          num_hidden_layers=layers, intermediate_size=1024, vocab_size=512,
+                          max_position_embeddings=8192, rope_theta=10000.0, attn_implementation="eager")
+    else:
+        from transformers import MistralConfig, MistralForCausalLM as M
+
+        cfg = MistralConfig(hidden_size=hidden, num_attention_heads=n_heads, num_key_value_heads=n_kv,
+                            num_hidden_layers=layers, intermediate_size=1024, vocab_size=512, head_dim=128,
+                            max_position_embeddings=8192, rope_theta=10000.0, sliding_window=None,
+                            attn_implementation="eager")
+    model = M(cfg).to(torch.bfloat16).eval()
+    return model
+
+
+SCHEDULE = [45, 1, 1, 30, 1, 1, 1, 20, 1, 1]
+
+
+@pytest.mark.parametrize("kind", ["llama", "mistral"])
+def test_patched_model_matches_oracle_model(kind):
+    model = tiny_model(kind)
+    gates = np.array([[0.9, 0.1], [0.2, 0.8]])
+    sink, recent = 4, 12
+    oracle = O.OracleModel(copy.deepcopy(model), gates, sink, recent)
+    enable_duo_attention_eval(model, gates, sink, recent)
+    model.cuda()
+    g = torch.Generator().manual_seed(1)
+    past_o, past_g = None, None
+    with torch.no_grad():
+        for S in SCHEDULE:
+            ids = torch.randint(0, 512, (1, S), generator=g)
+            lo, past_o = oracle(ids, past_o)
+            out = model(input_ids=ids.cuda(), past_key_values=past_g, use_cache=True)
+            past_g = out.past_key_values
+            assert out.logits.shape == (1, 1, 512) and out.logits.dtype == torch.float32
+            torch.testing.assert_close(out.logits.cpu(), lo, rtol=5e-2, atol=5e-2)
+            assert past_g.kv_seq_len == past_o[0][0].shape[2]
+
+
+def test_all_full_heads_equals_unpatched_hf():
+    model = tiny_model("llama", seed=3)
+    ref = copy.deepcopy(model).cuda()
+    gates = np.ones((2, 2))
+    enable_duo_attention_eval(model, gates, 4, 12)
+    model.cuda()
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(0, 512, (1, 80), generator=g).cuda()
+    with torch.no_grad():
+        want = ref(input_ids=ids).logits[:, -1:, :].float()
+        got = model(input_ids=ids, past_key_values=None, use_cache=True).logits
+    torch.testing.assert_close(got, want, rtol=5e-2, atol=5e-2)
+
+
+def test_static_cache_protocol_like_benchmark_static():
+    model = tiny_model("llama", seed=5)
+    gates = np.array([[1.0, 0.0], [0.0, 1.0]])
+    sink, recent = 8, 16
+    oracle = O.OracleModel(copy.deepcopy(model), gates, sink, recent)
+    enable_llama_duo_attention_static_kv_cache_eval(model, gates)
+    model.cuda()
+    cache = DuoAttentionStaticKVCache(model, gates, 1, 200, sink, recent)
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 512, (1, 150), generator=g)
+    with torch.no_grad():
+        past_o = None
+        for i in range(0, 150, 64):  # chunked prefill, benchmark_static.py:68-77
+            chunk = ids[:, i : i + 64]
+            lo, past_o = oracle(chunk, past_o)
+            out = model(input_ids=chunk.cuda(), past_key_values=cache, use_cache=True)
+        assert out.logits.dtype == torch.bfloat16  # llama static eval keeps bf16 logits
+        torch.testing.assert_close(out.logits.float().cpu(), lo, rtol=5e-2, atol=5e-2)
+        tok = lo.argmax(-1)
+        first = None
+        for _ in range(3):  # decode + evict_last(1): same logits every time (benchmark_static.py:96-103)
+            out = model(input_ids=tok.cuda(), past_key_values=cache, use_cache=True)
+            cache.evict_last(1)
+            if first is None:
+                first = out.logits.clone()
+                lo2, _ = oracle(tok, past_o)
+                torch.testing.assert_close(first.float().cpu(), lo2, rtol=5e-2, atol=5e-2)
+            else:
+                assert torch.equal(out.logits, first)
+        assert cache.kv_seq_len == 150
+        assert cache.memory_usage > 0
+        cache.clear()
+        assert cache.kv_seq_len == 0
+        with pytest.raises(ValueError, match="max size 200"):
+            model(input_ids=torch.zeros(1, 201, dtype=torch.long).cuda(), past_key_values=cache, use_cache=True)

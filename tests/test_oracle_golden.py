@@ -1,0 +1,100 @@
+"""Pin the CPU oracle against fixtures produced by the REFERENCE's own forward code
+(tests/golden/make_golden.py).  fp32, CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_cases as GC
+from oracle import duo_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def oracle_weights(case, data):
+    gate = data["gate"]
+    G = case["Hq"] // case["Hkv"]
+    wq, _ = O.reorder_rows_or_cols(data["wq"], None, gate, G * GC.D, "out")
+    wk, _ = O.reorder_rows_or_cols(data["wk"], None, gate, GC.D, "out")
+    wv, _ = O.reorder_rows_or_cols(data["wv"], None, gate, GC.D, "out")
+    wo, _ = O.reorder_rows_or_cols(data["wo"], None, gate, G * GC.D, "in")
+    return O.AttnWeights(wq, wk, wv, wo, case["Hq"], case["Hkv"], int((gate > 0.5).sum()))
+
+
+def run_oracle_layer(case, data):
+    w = oracle_weights(case, data)
+    outs = []
+    pos = 0
+    if case["path"] == "tuple":
+        rot = GC.hf_rotary(case)
+        past = None
+        for hs in data["chunks"]:
+            S = hs.shape[1]
+            cos, sin = rot(hs, torch.arange(pos, pos + S)[None])
+            out, past = O.tuple_forward(w, hs, cos, sin, past, case["sink"], case["recent"])
+            outs.append(out)
+            pos += S
+        lens = (past[0].shape[2], past[1].shape[2])
+    else:
+        cache = O.OracleStaticKVCache(1, case["Hq"], case["Hkv"], GC.D, [data["gate"].numpy()], data["B"],
+                                      case["max_size"], case["sink"], case["recent"])
+        for i, hs in enumerate(data["chunks"]):
+            S = hs.shape[1]
+            out = O.static_forward(w, hs, torch.arange(pos, pos + S)[None], cache, 0, case["theta"],
+                                   case.get("rope_factor") or 1.0)
+            outs.append(out)
+            pos += S
+            ev = case.get("evict_after", {}).get(i, 0)
+            if ev:
+                cache.evict_last(ev)
+                pos -= ev
+        lens = (cache.kv_seq_len, cache.streaming_kv_seq_len)
+    return torch.cat(outs, dim=1), lens
+
+
+@pytest.mark.parametrize("case", GC.LAYER_CASES, ids=[c["name"] for c in GC.LAYER_CASES])
+def test_oracle_matches_reference_forward(case):
+    gold = np.load(os.path.join(GOLD, f"layer_{case['name']}.npz"))
+    data = GC.make_layer_inputs(case)
+    assert abs(GC.checksum(data) - float(gold["checksum"])) < 1e-6 * abs(float(gold["checksum"])), "RNG drift"
+    with torch.no_grad():
+        out, lens = run_oracle_layer(case, data)
+    assert lens == (int(gold["final_full_len"]), int(gold["final_stream_len"]))
+    np.testing.assert_allclose(out.numpy(), gold["out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_closed_form_mask_equals_cache_semantics(seed):
+    """The chunk-relative streaming mask == cat/compaction semantics of the forward."""
+    rng = np.random.RandomState(seed)
+    sink, recent = int(rng.randint(0, 5)), int(rng.randint(1, 7))
+    Hq, Hkv, n_full = 4, 2, int(rng.randint(0, 3))
+    N = int(rng.randint(8, 40))
+    cuts = sorted(set(rng.randint(1, N, size=rng.randint(1, 8)).tolist()))
+    starts = [0] + cuts
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(1, N, Hq, 16, generator=g, dtype=torch.float64)
+    k = torch.randn(1, N, Hkv, 16, generator=g, dtype=torch.float64)
+    v = torch.randn(1, N, Hkv, 16, generator=g, dtype=torch.float64)
+    dense = O.dense_duo_attention(q, k, v, starts, n_full, Hq // Hkv, sink, recent)
+    past, outs = None, []
+    for a, b in zip(starts, starts[1:] + [N]):
+        o, past = O.tuple_attention_core(q[:, a:b], k[:, a:b], v[:, a:b], past, n_full, Hq // Hkv, sink, recent)
+        outs.append(o)
+    np.testing.assert_allclose(torch.cat(outs, 1).numpy(), dense.numpy(), rtol=2e-4, atol=2e-5)  # contract computes in fp32
+
+
+def test_flash_contract_bottom_right_and_gqa():
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(2, 3, 4, 8, generator=g)
+    k = torch.randn(2, 7, 2, 8, generator=g)
+    v = torch.randn(2, 7, 2, 8, generator=g)
+    out = O.flash_attn_contract(q, k, v, causal=True)
+    for b in range(2):
+        for h in range(4):
+            for i in range(3):
+                vis = i + 7 - 3 + 1
+                s = (q[b, i, h] @ k[b, :vis, h // 2].T) / 8 ** 0.5
+                ref = torch.softmax(s, -1) @ v[b, :vis, h // 2]
+                torch.testing.assert_close(out[b, i, h], ref, rtol=1e-5, atol=1e-6)
