@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""Benchmark of the DuoAttention hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[1] + the metric's 1M-context decode point):
+  Llama-3-8B-Instruct-Gradient-1048k architecture, random-init bf16 weights, real head pattern
+  attn_patterns/Llama-3-8B-Instruct-Gradient-1048k/... at sparsity 0.5 (128 retrieval + 128 streaming KV heads),
+  deploy-time sink=64 / recent=256, batch 1, synthetic random token ids.
+    * decode  : one token per step against a synthetically filled 1,048,576-token KV cache (evict_last(1) after
+                every step, the reference's benchmark_static.py:96-103 protocol)  -> `value` (tokens/s)
+    * prefill : 131,072 tokens in chunks of 32,768 through the same patched model        -> `prefill` object
+
+One process per GPU (`torchrun` for N > 1): KV heads are sharded across ranks (head-parallel TP, one NCCL
+all-reduce on the attention output and one on the MLP output per layer); total work is fixed -> "strong".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ctx 1048576] [--prefill-ctx 131072]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PATTERN_DIR = os.path.join(ROOT, "attn_patterns", "Llama-3-8B-Instruct-Gradient-1048k",
+                           "lr=0.02-reg=0.05-ctx=1000_32000-multi_passkey10")
+L3_8B = dict(hidden_size=4096, num_attention_heads=32, num_key_value_heads=8, head_dim=128, num_hidden_layers=32,
+             intermediate_size=14336, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=3580165449.0,
+             max_position_embeddings=1048576)
+SINK, RECENT = 64, 256
+METRIC = "decode tok/s @1M ctx (+ prefill tok/s @128K in `prefill`), Llama-3-8B, DuoAttention 50% retrieval heads"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ctx", type=int, default=1048576)
+    ap.add_argument("--prefill-ctx", type=int, default=131072)
+    ap.add_argument("--chunk", type=int, default=32768)
+    ap.add_argument("--prefill-reps", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=32, help="debug only: a run with fewer layers is not a valid number")
+    ap.add_argument("--no-prefill", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def head_pattern():
+    import numpy as np
+
+    from duo_attn.utils import load_attn_pattern, sparsify_attention_heads
+
+    gates, _, _ = load_attn_pattern(PATTERN_DIR)
+    np.random.seed(42)
+    mask, sp = sparsify_attention_heads(gates, None, 0.5)
+    return mask, float(sp)
+
+
+def decode_bytes_per_token(mask, ctx, elt=2, D=128):
+    """Algorithmic K+V bytes one decode step must read: retrieval heads read ctx+1 rows,
+    streaming heads sink+recent+1."""
+    n_f = mask.sum(1)
+    n_s = mask.shape[1] - n_f
+    return float(((n_f * (ctx + 1) + n_s * (SINK + RECENT + 1)) * 2 * D * elt).sum())
+
+
+def prefill_flops(mask, n_ctx, chunk, G=4, D=128):
+    """Algorithmic attention FLOPs (4*D per visible (q,k) pair per q-head; masked halves not credited)."""
+    W = SINK + RECENT
+    full_pairs = n_ctx * (n_ctx + 1) // 2
+    stream_pairs = 0
+    for cs in range(0, n_ctx, chunk):
+        c = min(chunk, n_ctx - cs)
+        past = cs if cs <= W else W
+        stream_pairs += c * past + c * (c + 1) // 2
+    n_f = int(mask.sum())
+    n_s = mask.size - n_f
+    return 4.0 * D * G * (n_f * full_pairs + n_s * stream_pairs)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm (the oracle port of the reference forward, timed on the host cores)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_sample(ctx, mask, threads=None):
+    """Time a bounded sample of ONE decode step of the reference's forward on the host: the attention of one
+    retrieval KV head (its 4 q-heads against ctx keys), one streaming KV head (321 keys) and one layer's
+    linear projections + MLP; scale to the whole model (128 + 128 KV heads, 32 layers).  Returns tokens/s."""
+    import torch
+
+    from oracle import duo_oracle as O
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    D, G = 128, 4
+    q = torch.randn(1, 1, G, D, generator=g).to(torch.bfloat16)
+    k = torch.randn(1, ctx + 1, 1, D, generator=g).to(torch.bfloat16)
+    v = torch.randn(1, ctx + 1, 1, D, generator=g).to(torch.bfloat16)
+    t0 = time.perf_counter()
+    O.flash_attn_contract(q, k, v, causal=True)
+    t_full = time.perf_counter() - t0
+    ks, vs = k[:, : SINK + RECENT + 1], v[:, : SINK + RECENT + 1]
+    t0 = time.perf_counter()
+    for _ in range(10):
+        O.flash_attn_contract(q, ks, vs, causal=True)
+    t_stream = (time.perf_counter() - t0) / 10
+    # one layer of bf16 GEMVs: qkv (6144x4096), o (4096x4096), gate/up (2x14336x4096), down (4096x14336)
+    x = torch.randn(1, 4096).to(torch.bfloat16)
+    ws = [torch.randn(n, m).to(torch.bfloat16) for n, m in ((6144, 4096), (4096, 4096), (28672, 4096))]
+    wd = torch.randn(4096, 14336).to(torch.bfloat16)
+    t0 = time.perf_counter()
+    for w in ws:
+        torch.nn.functional.linear(x, w)
+    torch.nn.functional.linear(torch.randn(1, 14336).to(torch.bfloat16), wd)
+    t_lin = time.perf_counter() - t0
+    n_f, n_s = int(mask.sum()), int(mask.size - mask.sum())
+    step_s = n_f * t_full + n_s * t_stream + mask.shape[0] * t_lin
+    return dict(tok_s=1.0 / step_s, t_full_head_s=t_full, t_stream_head_s=t_stream, t_layer_linear_s=t_lin,
+                step_s_extrapolated=step_s, cores=threads)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (oracle port; the reference package has no CPU attention of
+    its own and no tests — SURVEY.md §0/§4) on all host threads, same metric/config as our arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mask, sp = head_pattern()
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_reference_sample(args.ctx, mask))
+    best = max(vals, key=lambda r: r["tok_s"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": best["tok_s"], "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / best["tok_s"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, sp),
+        "cpu_baseline": {"value": best["tok_s"], "unit": "tokens/s", "cores": best["cores"], "kind": "port",
+                         "sample": "1 retrieval KV head @ctx + 1 streaming KV head + 1 layer of linears, "
+                                   "extrapolated to 128+128 heads x 32 layers", **{k: best[k] for k in
+                                   ("t_full_head_s", "t_stream_head_s", "t_layer_linear_s")}},
+        "e2e": {"value": best["tok_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, sparsity):
+    return {
+        "workload": f"Llama-3-8B-Instruct-Gradient-1048k arch (random init, bf16), DuoAttention pattern sparsity "
+                    f"{sparsity:.2f}, sink {SINK}/recent {RECENT}, batch 1: decode @ctx={args.ctx} "
+                    f"(evict_last(1) per step) + prefill {args.prefill_ctx} tokens in chunks of {args.chunk}",
+        "ctx": args.ctx, "prefill_ctx": args.prefill_ctx, "chunk": args.chunk, "layers": args.layers,
+        "parallelism": f"head-tp{args.gpus}",
+        "l2": "inputs larger than L2: every decode step streams >2 GB of KV per layer (126 MB L2), "
+              "prefill chunks stream the whole KV cache",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampling
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev_index):
+        self.idx = dev_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def build_model(args, mask, rank, world, dev):
+    """Random-init Llama-3-8B (or this rank's head-parallel shard of it) directly on the GPU, patched through
+    the drop-in API."""
+    import torch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+
+    from duo_attention_b200 import tp
+    from duo_attn.patch import enable_duo_attention_eval
+
+    cfgd = dict(L3_8B)
+    cfgd["num_hidden_layers"] = args.layers
+    plan = tp.plan_heads(mask[: args.layers], world)  # which (reordered) kv heads each rank owns, per layer
+    local_mask = plan.local_mask(rank)
+    cfgd["num_attention_heads"] = L3_8B["num_attention_heads"] // world
+    cfgd["num_key_value_heads"] = L3_8B["num_key_value_heads"] // world
+    cfgd["intermediate_size"] = L3_8B["intermediate_size"] // world
+    cfg = LlamaConfig(**cfgd, attn_implementation="eager")
+    with torch.device("meta"):
+        model = LlamaForCausalLM(cfg)
+    model = model.to(torch.bfloat16).to_empty(device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if prm.dim() == 1:
+                prm.fill_(1.0)
+            else:
+                prm.normal_(0.0, 0.02, generator=g)
+    model.model.rotary_emb = LlamaRotaryEmbedding(config=cfg, device=dev)
+    model.eval()
+    enable_duo_attention_eval(model, local_mask, SINK, RECENT)
+    if world > 1:
+        tp.install_allreduce(model)
+    return model, local_mask
+
+
+def fill_cache_synthetic(cache, ctx):
+    import torch
+
+    g = torch.Generator(device=cache.device).manual_seed(7)
+    for t in cache.tensors:
+        for name in ("full_k", "full_v", "ring_k", "ring_v"):
+            if t[name].numel():
+                t[name].normal_(generator=g)
+    for l in range(cache.num_layers):
+        cache.kv_seq_len_list[l] = ctx
+        cache.total_list[l] = ctx
+        cache.lo_list[l] = max(cache.sink_size, ctx - cache.recent_size)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from duo_attention_b200 import _C
+    from duo_attn.patch import DuoAttentionStaticKVCache
+
+    _C.load()  # fail loudly if the CUDA extension is missing
+    mask, sparsity = head_pattern()
+    mask = mask[: args.layers]
+    model, local_mask = build_model(args, mask, rank, world, dev)
+    vocab = L3_8B["vocab_size"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    result = {}
+    launches = 0
+    # ------------------------------------------------------------------ prefill @128K
+    cache = DuoAttentionStaticKVCache(model, local_mask, 1, args.ctx + 8, SINK, RECENT,
+                                      prefilling_chunk_size=args.chunk)
+    gcpu = torch.Generator().manual_seed(1)
+    if not args.no_prefill:
+        ids_host = torch.randint(0, vocab, (1, args.prefill_ctx), generator=gcpu).pin_memory()
+
+        def prefill_once(e2e):
+            cache.clear()
+            out = None
+            for i in range(0, args.prefill_ctx, args.chunk):
+                chunk = ids_host[:, i : i + args.chunk].to(dev, non_blocking=True)
+                out = model(input_ids=chunk, past_key_values=cache, use_cache=True)
+            tok = out.logits[:, -1, :].argmax(-1)
+            return int(tok.item()) if e2e else tok
+
+        with torch.no_grad():
+            prefill_once(False)  # warm-up (cuBLAS heuristics, TMA descriptors, allocator)
+            barrier()
+            c0 = cache.launch_count
+            times = []
+            for _ in range(args.prefill_reps):
+                cache.profile_events = []
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.nvtx.range_push("timed_prefill")
+                e0.record()
+                prefill_once(True)  # host ids in, host token out: this IS the end-to-end call
+                e1.record()
+                barrier()
+                torch.cuda.nvtx.range_pop()
+                times.append(max_over_ranks(e0.elapsed_time(e1)))
+                attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events)
+            cache.profile_events = None
+            launches_prefill = cache.launch_count - c0
+        ms = min(times)
+        fl = prefill_flops(mask, args.prefill_ctx, args.chunk)
+        peaks = load_peaks()
+        attn_ms = max_over_ranks(attn_ms)
+        result["prefill"] = {
+            "value": args.prefill_ctx / (ms / 1e3), "unit": "tokens/s", "ms_per_prefill": ms, "reps": args.prefill_reps,
+            "e2e": True, "h2d_bytes": int(args.prefill_ctx * 8), "d2h_bytes": 8,
+            "roofline": {"bound": "tensor", "achieved": fl / world / (attn_ms / 1e3) / 1e12 if attn_ms else None,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": (fl / world / (attn_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]) if attn_ms else None,
+                         "traffic": None, "attn_ms": attn_ms, "algorithmic_flops": fl,
+                         "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)"},
+            "gpu_launches": launches_prefill,
+        }
+
+    # ------------------------------------------------------------------ decode @1M
+    fill_cache_synthetic(cache, args.ctx)
+    tok_dev = torch.randint(0, vocab, (1, 1), generator=gcpu).to(dev)
+    tok_host = torch.randint(0, vocab, (1, 1), generator=gcpu).pin_memory()
+
+    def decode_step_resident():
+        out = model(input_ids=tok_dev, past_key_values=cache, use_cache=True)
+        cache.evict_last(1)
+        return out
+
+    def decode_step_e2e():
+        out = model(input_ids=tok_host.to(dev, non_blocking=True), past_key_values=cache, use_cache=True)
+        nxt = int(out.logits[:, -1, :].argmax(-1).item())  # D2H of the step's result
+        cache.evict_last(1)
+        return nxt
+
+    sampler = ClockSampler(local_rank)
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            decode_step_resident()
+        barrier()
+        # --- value: inputs resident in HBM
+        c0 = cache.launch_count
+        cache.profile_events = []
+        sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.nvtx.range_push("timed_decode")
+        e0.record()
+        for _ in range(args.steps):
+            decode_step_resident()
+        e1.record()
+        barrier()
+        torch.cuda.nvtx.range_pop()
+        clocks = sampler.stop()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = cache.launch_count - c0
+        attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events) / args.steps
+        n_attn = len(cache.profile_events) // args.steps
+        cache.profile_events = None
+        # --- e2e: host token in, host token out, every step
+        for _ in range(2):
+            decode_step_e2e()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            decode_step_e2e()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    ms_step = ms_total / args.steps
+    peaks = load_peaks()
+    by = decode_bytes_per_token(local_mask, args.ctx)  # this rank's algorithmic bytes
+    attn_ms_max = max_over_ranks(attn_ms)
+    achieved = by / (attn_ms / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": 1e3 / ms_step, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, sparsity),
+        "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": 8,
+                "d2h_bytes_per_step": 8},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "kernel": "duo_attn_mma_kernel (decode, all layers of one step)",
+                     "attn_ms_per_step": attn_ms, "attn_ms_per_step_max_rank": attn_ms_max,
+                     "launches_per_step": n_attn, "algorithmic_bytes_per_step": by,
+                     "peak_source": peaks["source"]},
+        "a100_published": {"decode_ms_per_tok_1M": 55.0, "note": "reference figure, 1xA100-80G, other hardware"},
+    }
+    line.update(result)
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cb = cpu_reference_sample(args.ctx, mask)
+        line["cpu_baseline"] = {"value": cb["tok_s"], "unit": "tokens/s", "cores": cb["cores"], "kind": "port",
+                                "sample": "oracle port of the reference forward: 1 retrieval KV head @ctx + 1 streaming "
+                                          "KV head + 1 layer of linears, extrapolated to 128+128 heads x 32 layers",
+                                "t_full_head_s": cb["t_full_head_s"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+if __name__ == "__main__":
+    main()

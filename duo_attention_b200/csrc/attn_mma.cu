@@ -381,24 +381,70 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
+  // Parallel merge: warp w takes splits w, w+4, ... (lane = 4 output dims), merges them online with 4
+  // independent loads in flight per row, then the 4 warps' partials are merged through shared memory.
   const float* po = p.ws_o + item * p.splits_full * (long long)(ROWS * 128);
   const float* pml = p.ws_ml + item * p.splits_full * (long long)(ROWS * 2);
-  for (int idx = tid; idx < rows_here * 64; idx += ATTN_THREADS) {
-    const int r = idx >> 6, d = (idx & 63) * 2;
+  float* cm_o = reinterpret_cast<float*>(smem);               // [4 warps][16][128]  (rows in groups of 16)
+  float* cm_ml = reinterpret_cast<float*>(smem + 80 * 1024);  // [4 warps][16][2]
+  for (int rg = 0; rg < rows_here; rg += 16) {
+  const int rg_n = min(16, rows_here - rg);
+  for (int rr = 0; rr < rg_n; ++rr) {
+    const int r = rg + rr;
+    float mm = -INFINITY, ll = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = warp; s0 < p.splits_full; s0 += 16) {
+      float ms[4], ls[4];
+      float4 vs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s2 = s0 + 4 * u;
+        const bool ok = s2 < p.splits_full;
+        const int sc2 = ok ? s2 : s0;
+        ms[u] = ok ? __ldcg(&pml[(sc2 * ROWS + r) * 2]) : -INFINITY;
+        ls[u] = __ldcg(&pml[(sc2 * ROWS + r) * 2 + 1]);
+        vs[u] = __ldcg(reinterpret_cast<const float4*>(&po[((long long)sc2 * ROWS + r) * 128 + lane * 4]));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ms[u] == -INFINITY) continue;
+        const float mn = fmaxf(mm, ms[u]);
+        const float fo = (mm == -INFINITY) ? 0.f : fast_exp2(mm - mn);
+        const float fn = fast_exp2(ms[u] - mn);
+        acc.x = acc.x * fo + vs[u].x * fn;
+        acc.y = acc.y * fo + vs[u].y * fn;
+        acc.z = acc.z * fo + vs[u].z * fn;
+        acc.w = acc.w * fo + vs[u].w * fn;
+        ll = ll * fo + ls[u] * fn;
+        mm = mn;
+      }
+    }
+    *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr) * 128 + lane * 4]) = acc;
+    if (lane == 0) {
+      cm_ml[(warp * 16 + rr) * 2] = mm;
+      cm_ml[(warp * 16 + rr) * 2 + 1] = ll;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rg_n * 64; idx += ATTN_THREADS) {
+    const int rr = idx >> 6, d = (idx & 63) * 2;
     float mm = -INFINITY;
-    for (int s2 = 0; s2 < p.splits_full; ++s2) mm = fmaxf(mm, __ldcg(&pml[(s2 * ROWS + r) * 2]));
+#pragma unroll
+    for (int w = 0; w < 4; ++w) mm = fmaxf(mm, cm_ml[(w * 16 + rr) * 2]);
     float a0f = 0.f, a1f = 0.f, ll = 0.f;
-    for (int s2 = 0; s2 < p.splits_full; ++s2) {
-      const float ms = __ldcg(&pml[(s2 * ROWS + r) * 2]);
-      if (ms == -INFINITY) continue;
-      const float f = fast_exp2(ms - mm);
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(&po[((long long)s2 * ROWS + r) * 128 + d]));
-      a0f += f * v.x;
-      a1f += f * v.y;
-      ll += f * __ldcg(&pml[(s2 * ROWS + r) * 2 + 1]);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = cm_ml[(w * 16 + rr) * 2];
+      if (mw == -INFINITY) continue;
+      const float f = fast_exp2(mw - mm);
+      a0f += f * cm_o[(w * 16 + rr) * 128 + d];
+      a1f += f * cm_o[(w * 16 + rr) * 128 + d + 1];
+      ll += f * cm_ml[(w * 16 + rr) * 2 + 1];
     }
     const float inv = ll > 0.f ? 1.f / ll : 0.f;
-    store_row_elem(r, d, a0f * inv, a1f * inv);
+    store_row_elem(rg + rr, d, a0f * inv, a1f * inv);
+  }
+  __syncthreads();
   }
   if (tid == 0) p.counters[item] = 0;  // leave the workspace ready for the next launch
 }

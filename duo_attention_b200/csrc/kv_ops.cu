@@ -7,7 +7,8 @@
 //   RoPE (fp32, flashinfer)  duo_attn/patch/flashinfer_utils.py:29-59
 //   append                   duo_attn/patch/static_kv_cache.py:109-125, 252-263
 //   ring commit              duo_attn/patch/static_kv_cache.py:127-167 / llama.py:273-290
-//   INT4 K1 / K2             demo/quantize_int4.cu:73-144 / :9-42
+//   INT4 K1 / K2             demo/quantize_int4.cu:73-144 / :9-42 (K2's __hadd(__hmul()) is contracted by nvcc
+//                            into one HFMA2 in the reference build — verified in its SASS — so K2 == fma)
 #include "duo_common.cuh"
 
 namespace duo {
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(256) dequant_int4_kernel(const uint8_t* packed
   const uint32_t q[4] = {b0 >> 4, b0 & 0xf, b1 >> 4, b1 & 0xf};
   Vec4<__half> o;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o.v[i] = __hadd(__hmul(__float2half((float)q[i]), s), z);
+  for (int i = 0; i < 4; ++i) o.v[i] = __hfma(__float2half((float)q[i]), s, z);  // as-built reference: HFMA2, one rounding
   *reinterpret_cast<Vec4<__half>*>(out + r * 128 + lane * 4) = o;
 }
 

@@ -108,6 +108,8 @@ class DuoKVCache:
         for l in range(num_layers):
             self.tensors.append(self._alloc_layer(l, self.full_cap_list[l], self.stage_cap_list[l]))
             self._make_handle(l)
+        self.launch_count = 0        # kernels of this library enqueued through this cache
+        self.profile_events = None   # set to [] to collect (start, end) CUDA events around every duo_attention
         ws = self.lib.duo_workspace_bytes(self.batch_size, num_kv_heads, self.num_kv_groups, _C.DECODE_MAX_Q)
         self.workspace = torch.zeros(ws, dtype=torch.uint8, device=device)
 
@@ -250,7 +252,7 @@ class DuoKVCache:
             raise RuntimeError("duo_attention_b200 kernels need CUDA tensors (no CPU fallback)")
         B, S, width = qkv.shape
         assert B == self.batch_size and width == (self.num_heads + 2 * self.num_kv_heads) * self.head_dim
-        assert qkv.stride(2) == 1 and qkv.stride(0) == S * qkv.stride(1), "qkv rows must be uniformly strided"
+        assert qkv.stride(2) == 1 and (B == 1 or qkv.stride(0) == S * qkv.stride(1)), "qkv rows must be uniformly strided"
         assert out.is_contiguous() and qkv.dtype == self.dtype and out.dtype == self.dtype
         self._ensure_room(l, S)
         st = self.state(l)
@@ -263,9 +265,16 @@ class DuoKVCache:
         sp = sin.data_ptr() if sin is not None else None
         _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode, S, stream))
         fn = lib.duo_attention_mma if force_mma else lib.duo_attention
+        if self.profile_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _C.check(fn(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), S, float(scale),
                     self.workspace.data_ptr(), self.workspace.numel(), stream))
+        if self.profile_events is not None:
+            e1.record()
+            self.profile_events.append((e0, e1))
         _C.check(lib.duo_stream_commit(h, C.byref(st), S, stream))
+        self.launch_count += 2 + (1 if self.num_streaming_kv_head_list[l] > 0 else 0)
         self.advance(l, S)
         return out
 

@@ -108,14 +108,21 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
     cos, sin = base.rotary_emb(inputs_embeds, position_ids)  # [1, S, D] in the activation dtype
     cos, sin = cos[0].contiguous(), sin[0].contiguous()
     h = inputs_embeds
+    tp_on = getattr(self, "_duo_tp", False)
+    if tp_on:
+        from ..tp import all_reduce_sum
     for idx, layer in enumerate(base.layers):
         res = h
         x = layer.input_layernorm(h)
         x = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
+        if tp_on:  # row-parallel o_proj partials -> one all-reduce per layer (NCCL over NVLink)
+            x = all_reduce_sum(x, self._duo_tp_group)
         h = res + x
         res = h
         x = layer.post_attention_layernorm(h)
         x = layer.mlp(x)
+        if tp_on:
+            x = all_reduce_sum(x, self._duo_tp_group)
         h = res + x
     h = base.norm(h[:, -1:, :])
     logits = self.lm_head(h)

@@ -50,8 +50,9 @@ def flash_attn_contract(q, k, v, causal=True, dropout_p=0.0, softmax_scale=None,
 
     q ``[B, Sq, Hq, D]``, k/v ``[B, Sk, Hkv, D]``; q-head ``i`` reads kv-head
     ``i // (Hq // Hkv)``; ``causal`` is BOTTOM-RIGHT aligned (row ``i`` sees keys
-    ``j <= i + Sk - Sq``); scale ``1/sqrt(D)``; softmax in fp32; P is cast to the input dtype
-    before the PV product (FA2 behaviour); output in the input dtype.
+    ``j <= i + Sk - Sq``); scale ``1/sqrt(D)``; softmax in fp32; the un-normalised P = exp(s - max) is
+    cast to the input dtype before the PV product and the division by the fp32 row sum happens last
+    (FA2 behaviour); output in the input dtype.
     Processes query rows in blocks so that [Sq, Sk] never has to exist at once.
     """
     assert dropout_p == 0.0
@@ -73,11 +74,16 @@ def flash_attn_contract(q, k, v, causal=True, dropout_p=0.0, softmax_scale=None,
             ii = torch.arange(r0, r1)
             masked = jj[None, :] > (ii[:, None] + (Sk - Sq))
             s = s.masked_fill(masked[None, None, None], float("-inf"))
-        p = torch.softmax(s, dim=-1)
-        # rows with no visible key (Sk < Sq top rows) -> FA2 returns 0
-        p = torch.nan_to_num(p, nan=0.0)
+        # FA2 arithmetic: P = exp(s - rowmax) is rounded to the input dtype UN-normalised, the row sum l is
+        # accumulated in fp32 from the unrounded P, and O = (P_rounded @ V) / l at the very end.
+        m = s.amax(dim=-1, keepdim=True)
+        m = torch.where(torch.isinf(m), torch.zeros_like(m), m)  # rows with no visible key -> output 0
+        p = torch.exp(s - m)
+        l = p.sum(dim=-1, keepdim=True)
         p = p.to(q.dtype).float().view(B, Hkv, G * (r1 - r0), Sk)
         o = torch.matmul(p, vdt.float())  # [B,Hkv,G*R,D]
+        l = l.view(B, Hkv, G * (r1 - r0), 1)
+        o = torch.where(l > 0, o / l.clamp_min(1e-38), torch.zeros_like(o))
         o = o.view(B, Hq, r1 - r0, D).permute(0, 2, 1, 3)
         out[:, r0:r1] = o.to(q.dtype)
     return out

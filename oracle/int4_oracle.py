@@ -7,8 +7,11 @@ Restates ``demo/quantize_int4.cu`` of the reference:
   ``q = clamp(roundf((x-zero)/scale), 0, 15)`` (roundf = half away from zero), pack
   ``(q_even << 4) | q_odd``; scale / zero stored as fp16 (round-to-nearest-even).
   NOTE the quantisation divides by the *fp32* scale, the fp16-rounded one is only stored.
-* ``dequantize_int4`` – kernel K2, quantize_int4.cu:9-42: ``out = __hadd(__hmul(half(q), s), z)``
-  i.e. two separate fp16 roundings.
+* ``dequantize_int4`` – kernel K2, quantize_int4.cu:9-42: ``out = __hadd(__hmul(half(q), s), z)``.
+  AS BUILT (nvcc, default -fmad=true, also under the reference's --use_fast_math) the mul+add pair is
+  contracted into a single ``HFMA2`` — checked in the SASS of oracle/_ref/quantize_int4_ref.so — so the
+  result is ``fp16(q*s + z)`` with ONE rounding.  The oracle restates that as-built behaviour
+  (``fused=True``); ``fused=False`` gives the literal two-rounding reading of the source.
 
 The reference builds with ``--use_fast_math`` (demo/int4_kv.py:54), which turns the fp32
 division into an approximate one: codes may differ by +-1 on (near-)exact .5 ties.  The oracle
@@ -48,14 +51,18 @@ def unpack_codes(packed: np.ndarray) -> np.ndarray:
     return out
 
 
-def dequantize_int4(packed: np.ndarray, scale: np.ndarray, zero: np.ndarray, group_size: int = 128):
-    """-> float16 ``[..., head_dim]``; fp16 multiply then fp16 add (two roundings)."""
+def dequantize_int4(packed: np.ndarray, scale: np.ndarray, zero: np.ndarray, group_size: int = 128, fused=True):
+    """-> float16 ``[..., head_dim]``; fused multiply-add, one rounding (see the module docstring)."""
     codes = unpack_codes(packed)
     hd = codes.shape[-1]
     ng = hd // group_size
     c = codes.reshape(*codes.shape[:-1], ng, group_size).astype(np.float16)
     s = scale.astype(np.float16)[..., None]
     z = zero.astype(np.float16)[..., None]
-    prod = (c * s).astype(np.float16)  # fp16 x fp16 is exact in fp32, then one RN to fp16
-    out = (prod + z).astype(np.float16)
+    if fused:
+        # exact in fp64 (<= 15 + 40 significant bits), then one correctly rounded conversion to fp16
+        out = (c.astype(np.float64) * s.astype(np.float64) + z.astype(np.float64)).astype(np.float16)
+    else:
+        prod = (c * s).astype(np.float16)  # fp16 x fp16 is exact in fp32, then one RN to fp16
+        out = (prod + z).astype(np.float16)
     return out.reshape(*codes.shape[:-1], hd)

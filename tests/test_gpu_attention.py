@@ -10,6 +10,7 @@ import torch
 from duo_attention_b200 import _C
 from duo_attention_b200.kv_cache import DuoKVCache
 from oracle import duo_oracle as O
+from parity import assert_parity
 
 pytestmark = pytest.mark.gpu
 D = 128
@@ -44,8 +45,7 @@ def run_schedule(Hq, Hkv, n_full, sink, recent, chunks, B=1, dtype=torch.bfloat1
         got = out.float().cpu()
         outs.append(got)
         if check:
-            torch.testing.assert_close(got, ref.float(), rtol=RTOL, atol=ATOL,
-                                       msg=lambda m: f"chunk {i} (len {S}, past {cache.kv_seq_len - S}): {m}")
+            assert_parity(got, ref, f"chunk {i} (len {S}, past {cache.kv_seq_len - S})")
         worst = max(worst, (got - ref.float()).abs().max().item())
         ev = (evict_after or {}).get(i, 0)
         if ev:
@@ -111,8 +111,7 @@ def test_evict_last_like_the_benchmark():
 
 def test_split_kv_long_context_decode():
     # one retrieval kv head, 20k keys: ~150+ key splits merged by the last CTA in the same launch
-    worst, _ = run_schedule(4, 1, 1, 64, 256, [20000, 1, 1, 3, 1], seed=11, stage_cap=20000)
-    assert worst < 5e-3
+    run_schedule(4, 1, 1, 64, 256, [20000, 1, 1, 3, 1], seed=11, stage_cap=20000)
 
 
 def test_split_kv_with_streaming_heads_long():
@@ -195,15 +194,17 @@ def test_full_size_decode_properties(N):
     qz = qkv.clone()
     qz[..., : Hq * D] = 0
     qkv.copy_(qz)
-    o = decode()[0, 0]
     vnew = qz[0, 0, (Hq + Hkv) * D :].view(Hkv, D).float()
-    for h in range(Hq):
-        kvh = h // 4
+    # expected means are taken BEFORE the call: the ring commit that follows the attention overwrites one slot
+    means = []
+    for kvh in range(Hkv):
         if kvh < n_full:
-            mean = (t["full_v"][0, kvh, :N].float().sum(0) + vnew[kvh]) / (N + 1)
+            means.append((t["full_v"][0, kvh, :N].float().sum(0) + vnew[kvh]) / (N + 1))
         else:
-            mean = (t["ring_v"][0, kvh - n_full, :W].float().sum(0) + vnew[kvh]) / (W + 1)
-        torch.testing.assert_close(o[h], mean, rtol=1e-2, atol=1e-3)
+            means.append((t["ring_v"][0, kvh - n_full, :W].float().sum(0) + vnew[kvh]) / (W + 1))
+    o = decode()[0, 0]
+    for h in range(Hq):
+        torch.testing.assert_close(o[h], means[h // 4], rtol=1e-2, atol=1e-3)
     qkv.copy_(qkv_backup)
 
     # (3) one key with an overwhelming logit -> output == that key's V row, wherever it sits

@@ -30,14 +30,16 @@ def test_round_trip_error_bounded_by_half_step():
     assert (np.take_along_axis(codes, x.argmax(-1)[..., None], -1) == 15).all()
 
 
-def test_dequant_uses_two_fp16_roundings():
+def test_dequant_rounding_modes():
     p = np.full((1, 64), 0x7B, dtype=np.uint8)  # codes 7, 11
     s = np.array([[0.333251953125]], dtype=np.float16)
     z = np.array([[-1.7001953125]], dtype=np.float16)
-    y = Q.dequantize_int4(p, s, z)
-    for code, got in ((7, y[0, 0]), (11, y[0, 1])):
+    y = Q.dequantize_int4(p, s, z)                 # as built: fused, one rounding
+    y2 = Q.dequantize_int4(p, s, z, fused=False)   # literal source reading: two roundings
+    for code, got, got2 in ((7, y[0, 0], y2[0, 0]), (11, y[0, 1], y2[0, 1])):
+        assert got == np.float16(np.float64(code) * np.float64(s[0, 0]) + np.float64(z[0, 0]))
         prod = np.float16(np.float32(code) * np.float32(s[0, 0]))
-        assert got == np.float16(np.float32(prod) + np.float32(z[0, 0]))
+        assert got2 == np.float16(np.float32(prod) + np.float32(z[0, 0]))
 
 
 def test_constant_group_is_stable():
