@@ -28,8 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-PATTERN_DIR = os.path.join(ROOT, "attn_patterns", "Llama-3-8B-Instruct-Gradient-1048k",
-                           "lr=0.02-reg=0.05-ctx=1000_32000-multi_passkey10")
+def pattern_dir(name):
+    base = os.path.join(ROOT, "attn_patterns", name)
+    return os.path.join(base, sorted(os.listdir(base))[0])
 L3_8B = dict(hidden_size=4096, num_attention_heads=32, num_key_value_heads=8, head_dim=128, num_hidden_layers=32,
              intermediate_size=14336, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=3580165449.0,
              max_position_embeddings=1048576)
@@ -48,28 +49,33 @@ def parse():
     ap.add_argument("--chunk", type=int, default=32768)
     ap.add_argument("--prefill-reps", type=int, default=2)
     ap.add_argument("--layers", type=int, default=32, help="debug only: a run with fewer layers is not a valid number")
+    ap.add_argument("--kv-format", default="bf16", choices=["bf16", "int4"],
+                    help="int4 = BASELINE configs[3]: fp16 activations, INT4 KV with fused dequant (linears stay 16-bit: "
+                         "the reference's W8A8 linears are QServe's, absent here)")
+    ap.add_argument("--pattern", default="Llama-3-8B-Instruct-Gradient-1048k")
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fa2", action="store_true", help="skip the same-box FlashAttention-2 micro-comparison")
     return ap.parse_args()
 
 
-def head_pattern():
+def head_pattern(name="Llama-3-8B-Instruct-Gradient-1048k"):
     import numpy as np
 
     from duo_attn.utils import load_attn_pattern, sparsify_attention_heads
 
-    gates, _, _ = load_attn_pattern(PATTERN_DIR)
+    gates, _, _ = load_attn_pattern(pattern_dir(name))
     np.random.seed(42)
     mask, sp = sparsify_attention_heads(gates, None, 0.5)
     return mask, float(sp)
 
 
-def decode_bytes_per_token(mask, ctx, elt=2, D=128):
+def decode_bytes_per_token(mask, ctx, row_bytes=256):
     """Algorithmic K+V bytes one decode step must read: retrieval heads read ctx+1 rows,
-    streaming heads sink+recent+1."""
+    streaming heads sink+recent+1; a row is 256 B (bf16) or 64+2+2 = 68 B (INT4 + fp16 scale/zero)."""
     n_f = mask.sum(1)
     n_s = mask.shape[1] - n_f
-    return float(((n_f * (ctx + 1) + n_s * (SINK + RECENT + 1)) * 2 * D * elt).sum())
+    return float(((n_f * (ctx + 1) + n_s * (SINK + RECENT + 1)) * 2 * row_bytes).sum())
 
 
 def prefill_flops(mask, n_ctx, chunk, G=4, D=128):
@@ -133,7 +139,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mask, sp = head_pattern()
+    mask, sp = head_pattern(args.pattern)
     vals = []
     for _ in range(max(1, min(args.steps, 3))):
         vals.append(cpu_reference_sample(args.ctx, mask))
@@ -157,7 +163,7 @@ def workload_config(args, sparsity):
         "workload": f"Llama-3-8B-Instruct-Gradient-1048k arch (random init, bf16), DuoAttention pattern sparsity "
                     f"{sparsity:.2f}, sink {SINK}/recent {RECENT}, batch 1: decode @ctx={args.ctx} "
                     f"(evict_last(1) per step) + prefill {args.prefill_ctx} tokens in chunks of {args.chunk}",
-        "ctx": args.ctx, "prefill_ctx": args.prefill_ctx, "chunk": args.chunk, "layers": args.layers,
+        "pattern": args.pattern, "kv_format": args.kv_format, "ctx": args.ctx, "prefill_ctx": args.prefill_ctx, "chunk": args.chunk, "layers": args.layers,
         "parallelism": f"head-tp{args.gpus}",
         "l2": "inputs larger than L2: every decode step streams >2 GB of KV per layer (126 MB L2), "
               "prefill chunks stream the whole KV cache",
@@ -233,7 +239,7 @@ def build_model(args, mask, rank, world, dev):
     cfg = LlamaConfig(**cfgd, attn_implementation="eager")
     with torch.device("meta"):
         model = LlamaForCausalLM(cfg)
-    model = model.to(torch.bfloat16).to_empty(device=dev)
+    model = model.to(torch.float16 if args.kv_format == "int4" else torch.bfloat16).to_empty(device=dev)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     with torch.no_grad():
         for name, prm in model.named_parameters():
@@ -255,7 +261,13 @@ def fill_cache_synthetic(cache, ctx):
     g = torch.Generator(device=cache.device).manual_seed(7)
     for t in cache.tensors:
         for name in ("full_k", "full_v", "ring_k", "ring_v"):
-            if t[name].numel():
+            if not t[name].numel():
+                continue
+            if t[name].dtype == torch.uint8:  # INT4: random codes, scale/zero of a unit-normal row
+                t[name].random_(0, 256, generator=g)
+                t[name + "_scale"].fill_(0.4)
+                t[name + "_zero"].fill_(-3.0)
+            else:
                 t[name].normal_(generator=g)
     for l in range(cache.num_layers):
         cache.kv_seq_len_list[l] = ctx
@@ -284,7 +296,7 @@ def main():
     from duo_attn.patch import DuoAttentionStaticKVCache
 
     _C.load()  # fail loudly if the CUDA extension is missing
-    mask, sparsity = head_pattern()
+    mask, sparsity = head_pattern(args.pattern)
     mask = mask[: args.layers]
     model, local_mask = build_model(args, mask, rank, world, dev)
     vocab = L3_8B["vocab_size"]
@@ -305,7 +317,8 @@ def main():
     launches = 0
     # ------------------------------------------------------------------ prefill @128K
     cache = DuoAttentionStaticKVCache(model, local_mask, 1, args.ctx + 8, SINK, RECENT,
-                                      prefilling_chunk_size=args.chunk)
+                                      prefilling_chunk_size=args.chunk if not args.no_prefill else 64,
+                                      kv_format="int4" if args.kv_format == "int4" else "same")
     gcpu = torch.Generator().manual_seed(1)
     if not args.no_prefill:
         ids_host = torch.randint(0, vocab, (1, args.prefill_ctx), generator=gcpu).pin_memory()
@@ -406,13 +419,13 @@ def main():
 
     ms_step = ms_total / args.steps
     peaks = load_peaks()
-    by = decode_bytes_per_token(local_mask, args.ctx)  # this rank's algorithmic bytes
+    by = decode_bytes_per_token(local_mask, args.ctx, 68 if args.kv_format == "int4" else 256)  # this rank's bytes
     attn_ms_max = max_over_ranks(attn_ms)
     achieved = by / (attn_ms / 1e3) / 1e9
     line = {
         "metric": METRIC, "value": 1e3 / ms_step, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "fp16 (INT4 KV)" if args.kv_format == "int4" else "bf16", "data": "synthetic",
         "config": workload_config(args, sparsity),
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": 8,
                 "d2h_bytes_per_step": 8},
@@ -420,13 +433,21 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                     "kernel": "duo_attn_mma_kernel (decode, all layers of one step)",
+                     "kernel": ("duo_attn_int4_kernel" if args.kv_format == "int4" else "duo_attn_mma_kernel")
+                               + " (decode, all layers of one step)",
                      "attn_ms_per_step": attn_ms, "attn_ms_per_step_max_rank": attn_ms_max,
                      "launches_per_step": n_attn, "algorithmic_bytes_per_step": by,
                      "peak_source": peaks["source"]},
         "a100_published": {"decode_ms_per_tok_1M": 55.0, "note": "reference figure, 1xA100-80G, other hardware"},
     }
     line.update(result)
+    if world == 1 and args.kv_format == "bf16" and not args.no_fa2:
+        del cache
+        torch.cuda.empty_cache()
+        try:
+            line["fa2_same_box"] = fa2_same_box(dev, args.ctx, args.chunk, args.prefill_ctx)
+        except Exception as e:  # the comparison is informative, never fatal
+            line["fa2_same_box"] = {"error": repr(e)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_sample(args.ctx, mask)
         line["cpu_baseline"] = {"value": cb["tok_s"], "unit": "tokens/s", "cores": cb["cores"], "kind": "port",
@@ -437,6 +458,110 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def fa2_same_box(dev, ctx, chunk, prefill_ctx):
+    """The reference's own GPU attention on this box: llama.py:374-421 restated with the INSTALLED flash_attn_func
+    (FA2 recompiled for sm_100, mma.sync) on token-major caches, timed per layer with the
+    reference's bench protocol (CUDA events), next to our fused launch on the same shapes.  Micro-benchmark of
+    the attention op only (one layer, n_full = 4 of 8 KV heads)."""
+    import ctypes as C
+
+    import torch
+
+    from duo_attention_b200 import _C
+    from duo_attention_b200.kv_cache import DuoKVCache
+
+    try:
+        from flash_attn import flash_attn_func
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": repr(e)}
+    Hq, Hkv, nf, D, G = 32, 8, 4, 128, 4
+    W = SINK + RECENT
+    res = {}
+    g = torch.Generator(device=dev).manual_seed(3)
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- decode at ctx: reference = FA2(full q-heads, token-major full cache) + FA2(streaming) + cat
+    fk = torch.randn(1, ctx + 1, nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    fv = torch.randn(1, ctx + 1, nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    sk = torch.randn(1, W + 1, Hkv - nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    sv = torch.randn(1, W + 1, Hkv - nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    q = torch.randn(1, 1, Hq, D, device=dev, dtype=torch.bfloat16, generator=g)
+
+    def ref_decode():
+        a = flash_attn_func(q[:, :, : nf * G], fk, fv, causal=True)
+        b = flash_attn_func(q[:, :, nf * G :], sk, sv, causal=True)
+        return torch.cat([a, b], dim=2)
+
+    t_ref = timeit(ref_decode, 10)
+    del fk, fv
+    cache = DuoKVCache(1, Hq, Hkv, D, [nf], 1, ctx + 8, SINK, RECENT, torch.bfloat16, dev)
+    for n in ("full_k", "full_v", "ring_k", "ring_v"):
+        cache.tensors[0][n].normal_(generator=g)
+    qkv = torch.randn(1, 1, (Hq + 2 * Hkv) * D, device=dev, dtype=torch.bfloat16, generator=g)
+    out = torch.empty(1, 1, Hq, D, device=dev, dtype=torch.bfloat16)
+    st = _C.CacheState(ctx, ctx, ctx - RECENT)
+    stream = torch.cuda.current_stream().cuda_stream
+    lib, h = cache.lib, cache.handles[0]
+    _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), None, None, 0, 1, stream))
+
+    def ours_decode():
+        _C.check(lib.duo_attention(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), 1, D ** -0.5,
+                                   cache.workspace.data_ptr(), cache.workspace.numel(), stream))
+
+    t_ours = timeit(ours_decode, 10)
+    res["decode_layer_nfull4"] = {"ctx": ctx, "fa2_ms": t_ref, "ours_ms": t_ours, "speedup": t_ref / t_ours}
+    del cache
+    # ---- prefill: last chunk of the 128K prefill (chunk tokens against prefill_ctx keys)
+    past = prefill_ctx - chunk
+    fk = torch.randn(1, prefill_ctx, nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    fv = torch.randn(1, prefill_ctx, nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    sk = torch.randn(1, W + chunk, Hkv - nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    sv = torch.randn(1, W + chunk, Hkv - nf, D, device=dev, dtype=torch.bfloat16, generator=g)
+    q = torch.randn(1, chunk, Hq, D, device=dev, dtype=torch.bfloat16, generator=g)
+
+    def ref_prefill():
+        a = flash_attn_func(q[:, :, : nf * G], fk, fv, causal=True)
+        b = flash_attn_func(q[:, :, nf * G :], sk, sv, causal=True)
+        return torch.cat([a, b], dim=2)
+
+    t_ref = timeit(ref_prefill, 3)
+    del fk, fv, sk, sv
+    cache = DuoKVCache(1, Hq, Hkv, D, [nf], 1, prefill_ctx + 8, SINK, RECENT, torch.bfloat16, dev, stage_cap=chunk)
+    for n in ("full_k", "full_v", "ring_k", "ring_v"):
+        cache.tensors[0][n].normal_(generator=g)
+    qkv = torch.randn(1, chunk, (Hq + 2 * Hkv) * D, device=dev, dtype=torch.bfloat16, generator=g)
+    out = torch.empty(1, chunk, Hq, D, device=dev, dtype=torch.bfloat16)
+    st = _C.CacheState(past, past, past - RECENT)
+    lib, h = cache.lib, cache.handles[0]
+    _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), None, None, 0, chunk, stream))
+
+    def ours_prefill():
+        _C.check(lib.duo_attention(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), chunk, D ** -0.5,
+                                   cache.workspace.data_ptr(), cache.workspace.numel(), stream))
+
+    t_ours = timeit(ours_prefill, 3)
+    pairs_full = chunk * past + chunk * (chunk + 1) // 2
+    pairs_stream = chunk * W + chunk * (chunk + 1) // 2
+    fl = 4.0 * D * G * (nf * pairs_full + (Hkv - nf) * pairs_stream)
+    res["prefill_layer_nfull4_last_chunk"] = {
+        "chunk": chunk, "past": past, "fa2_ms": t_ref, "ours_ms": t_ours, "speedup": t_ref / t_ours,
+        "fa2_tflops": fl / t_ref / 1e9, "ours_tflops": fl / t_ours / 1e9}
+    del cache
+    torch.cuda.empty_cache()
+    return res
 
 
 def load_peaks():

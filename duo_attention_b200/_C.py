@@ -15,6 +15,7 @@ DUO_OK, DUO_EINVAL, DUO_EOVERFLOW, DUO_ECUDA, DUO_EWORKSPACE = 0, -1, -2, -3, -4
 DT_BF16, DT_FP16 = 0, 1
 KV_SAME, KV_INT4 = 0, 1
 ROPE_NONE, ROPE_HF, ROPE_FP32 = 0, 1, 2
+ROPE_SKIP_Q = 0x100
 DECODE_MAX_Q = 16
 
 # every symbol include/duo_b200.h declares (checked by tests/test_cabi_symbols.py)

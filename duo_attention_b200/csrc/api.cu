@@ -81,6 +81,14 @@ static int encode_kv_map(CUtensorMap* m, void* base, int dtype, long long slots,
   return DUO_OK;
 }
 
+// first staging slot of the streaming cache: right after the ring for 16-bit caches (TMA takes any
+// coordinate); rounded up to a multiple of 64 for INT4 so that every 64-key tile (and its scale/zero rows)
+// starts 16-byte aligned for cp.async.
+int stage_offset(const duo_layer_desc& d) {
+  const int W = d.sink + d.recent;
+  return d.kv_format == DUO_KV_INT4 ? (W + 63) / 64 * 64 : W;
+}
+
 }  // namespace duo
 
 using namespace duo;
@@ -112,6 +120,13 @@ int duo_layer_create(const duo_layer_desc* desc, duo_layer** out) {
   if (desc->kv_format == DUO_KV_INT4 && desc->dtype != DUO_DT_FP16) {
     set_error("duo_layer_create: INT4 KV needs fp16 activations (demo/run_duo_w8a8kv4.py:41-45)");
     return DUO_EINVAL;
+  }
+  if (desc->kv_format == DUO_KV_INT4) {
+    const long long ring_slots = (long long)stage_offset(*desc) + desc->stage_cap;
+    if (desc->full_cap % 8 != 0 || ring_slots % 8 != 0) {
+      set_error("duo_layer_create: INT4 caches need full_cap and ring slots (%lld) to be multiples of 8", ring_slots);
+      return DUO_EINVAL;
+    }
   }
   duo_layer* L = new (std::nothrow) duo_layer();
   if (!L) {
@@ -185,11 +200,11 @@ int duo_rope_append(const duo_layer* layer, const duo_cache_state* st, void* qkv
                     const void* cos, const void* sin, int32_t rope_mode, int32_t q_len, void* stream) {
   int rc = check_chunk(layer, st, q_len, "duo_rope_append");
   if (rc) return rc;
-  if (!qkv || (rope_mode != DUO_ROPE_NONE && (!cos || !sin))) {
+  if (!qkv || ((rope_mode & 0xff) != DUO_ROPE_NONE && (!cos || !sin))) {
     set_error("duo_rope_append: null buffer");
     return DUO_EINVAL;
   }
-  if (rope_mode < DUO_ROPE_NONE || rope_mode > DUO_ROPE_FP32) {
+  if ((rope_mode & 0xff) < DUO_ROPE_NONE || (rope_mode & 0xff) > DUO_ROPE_FP32 || (rope_mode & ~(0xff | DUO_ROPE_SKIP_Q))) {
     set_error("duo_rope_append: bad rope_mode %d", rope_mode);
     return DUO_EINVAL;
   }

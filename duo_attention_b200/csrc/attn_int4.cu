@@ -1,9 +1,631 @@
-// INT4-KV attention (placeholder)
+// Mixed-head attention over an INT4 KV cache with the dequantisation FOLDED INTO THE K/V LOAD.
+//
+// The reference dequantises the whole cache to an fp16 scratch buffer on every layer of every step
+// (demo/int4_kv.py:373-436: an O(ctx) write + re-read) and then calls flash_attn_func on it
+// (demo/w8a8kv4_llama.py:239-274).  Here the packed nibbles go HBM -> smem -> registers -> tensor cores and the
+// per-row scale / zero-point are applied algebraically on the 16 x keys logits / 16 x 128 outputs instead of on
+// the keys x 128 elements:
+//
+//   S[r,j] = s_j * (Q_r . c_j) + z_j * sum(Q_r)                 c_j = 4-bit codes of key j
+//   O[r,:] = sum_j (p_rj s_j) c_j  +  sum_j p_rj z_j
+//
+// nibble -> fp16 costs 5 ALU ops per 8 nibbles: (w & 0x000f000f) | 0x64006400 is the half2 (1024+c_a, 1024+c_b)
+// and (w & 0x00f000f0) | 0x64006400 is (1024+16 c_a', 1024+16 c_b'); the +1024 offsets and the x16 are removed
+// algebraically (Q pre-scaled by 1/16 on the "high nibble" slots, offsets subtracted per row), so no per-element
+// subtract / multiply is ever issued.  Because a dot product is permutation invariant the head_dim order inside
+// a k16 step is chosen to match what these masks produce; V codes are transposed for the PV product by
+// ldmatrix.trans on 16-bit units (4 codes of one key), which lands the same head_dim column of two adjacent
+// keys in one register - exactly the (0x000f000f) pattern again.
+//
+// Tiles (64 keys: 4 KB K + 4 KB V + 4 x 128 B scale/zero = 8.5 KB instead of 32 KB) are fetched with 16 B
+// cp.async (zero-fill beyond the valid rows) into a 4-stage ring.  Same work decomposition, masks, split-KV merge
+// and variants as attn_mma.cu.  Activations are fp16 (the reference's INT4 demo runs in fp16).
 #include "duo_common.cuh"
+
 namespace duo {
-int launch_attn_int4(const duo_layer*, const duo_cache_state*, const void*, long long, void*, int, float, void*, size_t,
-                     cudaStream_t) {
-  set_error("INT4 attention kernel not built");
-  return DUO_EINVAL;
+
+constexpr int I4_TILE = 64;
+constexpr int I4_STAGES = 4;
+constexpr int I4_PACK_BYTES = I4_TILE * 64;                   // one packed K or V tile
+constexpr int I4_STAGE_BYTES = 2 * I4_PACK_BYTES + 4 * 128;   // + k_scale, k_zero, v_scale, v_zero
+constexpr int I4_THREADS = 128;
+constexpr int I4_MERGE_BYTES = 96 * 1024;                     // smem the split-KV merge needs (see attn_mma.cu)
+constexpr int I4_SMEM_BYTES = (I4_STAGES * I4_STAGE_BYTES > I4_MERGE_BYTES ? I4_STAGES * I4_STAGE_BYTES : I4_MERGE_BYTES) + 128;
+
+struct I4Params {
+  const void* q;
+  void* out;
+  long long q_tok_stride, q_batch_stride, out_batch_stride;
+  int q_len, n_q_heads, group, n_full, n_stream, batch;
+  int sink, recent, W, stage_off;
+  long long full_len, total, lo;
+  long long full_cap, ring_slots;
+  float scale_log2;
+  int splits_full, keys_per_split, n_rb, cache_scan;
+  float* ws_o;
+  float* ws_ml;
+  int* counters;
+  const uint8_t *full_k, *full_v, *ring_k, *ring_v;
+  const __half *fks, *fkz, *fvs, *fvz, *rks, *rkz, *rvs, *rvz;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint32_t lop_lo(uint32_t w) {  // half2(1024 + nib[bits 0-3], 1024 + nib[bits 16-19])
+  return (w & 0x000f000fu) | 0x64006400u;
+}
+__device__ __forceinline__ uint32_t lop_hi(uint32_t w) {  // half2(1024 + 16 nib[bits 4-7], 1024 + 16 nib[bits 20-23])
+  return (w & 0x00f000f0u) | 0x64006400u;
+}
+
+template <int KEY_WARPS>
+__global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Params p) {
+  constexpr int ROW_WARPS = 4 / KEY_WARPS;
+  constexpr int ROWS = 16 * ROW_WARPS;
+  constexpr int KPW = I4_TILE / KEY_WARPS;
+  constexpr int NT = KPW / 8;
+  using Op = MmaOp<__half>;
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int b = blockIdx.y;
+
+  // ---- work item (same enumeration as attn_mma.cu) ----------------------------------------------
+  const int n_full_items = p.n_full * p.n_rb * p.splits_full;
+  int kvh, rb, split;
+  bool is_full;
+  if ((int)blockIdx.x < n_full_items) {
+    is_full = true;
+    int x = blockIdx.x;
+    split = x % p.splits_full;
+    x /= p.splits_full;
+    rb = p.n_rb - 1 - (x % p.n_rb);
+    kvh = x / p.n_rb;
+  } else {
+    is_full = false;
+    int x = blockIdx.x - n_full_items;
+    rb = p.n_rb - 1 - (x % p.n_rb);
+    kvh = p.n_full + x / p.n_rb;
+    split = 0;
+  }
+  const int rows_total = p.group * p.q_len;
+  const int row0 = rb * ROWS;
+  const int rows_here = min(ROWS, rows_total - row0);
+  const int tok_max = (row0 + rows_here - 1) / p.group;
+  long long a0, a1, b0 = 0, b1 = 0, base, slots;
+  const uint8_t *gk, *gv;
+  const __half *gks, *gkz, *gvs, *gvz;
+  if (is_full) {
+    base = p.full_len;
+    const long long nkeys = p.full_len + tok_max + 1;
+    a0 = (long long)split * p.keys_per_split;
+    a1 = min(nkeys, a0 + (long long)p.keys_per_split);
+    if (a1 < a0) a1 = a0;
+    slots = p.full_cap;
+    const long long hrow = ((long long)b * p.n_full + kvh) * p.full_cap;
+    gk = p.full_k + hrow * 64;
+    gv = p.full_v + hrow * 64;
+    gks = p.fks + hrow;
+    gkz = p.fkz + hrow;
+    gvs = p.fvs + hrow;
+    gvz = p.fvz + hrow;
+  } else {
+    base = p.stage_off;
+    a0 = 0;
+    a1 = p.cache_scan;
+    b0 = p.stage_off;
+    b1 = (long long)p.stage_off + tok_max + 1;
+    slots = p.ring_slots;
+    const long long hrow = ((long long)b * p.n_stream + (kvh - p.n_full)) * p.ring_slots;
+    gk = p.ring_k + hrow * 64;
+    gv = p.ring_v + hrow * 64;
+    gks = p.rks + hrow;
+    gkz = p.rkz + hrow;
+    gvs = p.rvs + hrow;
+    gvz = p.rvz + hrow;
+  }
+  const int nA = (int)((a1 - a0 + I4_TILE - 1) / I4_TILE);
+  const int nB = (int)((b1 - b0 + I4_TILE - 1) / I4_TILE);
+  const int n_tiles = nA + nB;
+  auto tile_start = [&](int i) -> long long {
+    return i < nA ? a0 + (long long)i * I4_TILE : b0 + (long long)(i - nA) * I4_TILE;
+  };
+  auto tile_end = [&](int i) -> long long { return i < nA ? a1 : b1; };
+
+  // ---- cooperative tile loader: 16 B cp.async, zero-fill for rows past the segment / allocation ----
+  auto issue = [&](int i) {
+    if (i < n_tiles) {
+      const long long j0 = tile_start(i);
+      const long long lim = min(tile_end(i), slots);  // rows >= lim are not read (zero-filled)
+      const uint32_t sbase = smem_u32(smem + (i % I4_STAGES) * I4_STAGE_BYTES);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int chunk = tid + it * I4_THREADS;  // 0..255: row = chunk/4, c = chunk%4
+        const int r = chunk >> 2, c = chunk & 3;
+        const bool ok = (j0 + r) < lim;
+        const long long srow = ok ? (j0 + r) : 0;
+        const uint32_t doff = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+        cp_async16(sbase + doff, gk + srow * 64 + c * 16, ok ? 16 : 0);
+        cp_async16(sbase + I4_PACK_BYTES + doff, gv + srow * 64 + c * 16, ok ? 16 : 0);
+      }
+      if (tid < 32) {
+        const int arr = tid >> 3, qd = tid & 7;  // 4 arrays x 8 chunks of 8 rows
+        const __half* src = arr == 0 ? gks : arr == 1 ? gkz : arr == 2 ? gvs : gvz;
+        const long long r0 = j0 + qd * 8;
+        long long nb = (lim - r0) * 2;
+        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+        cp_async16(sbase + 2 * I4_PACK_BYTES + arr * 128 + qd * 16, src + (nb > 0 ? r0 : 0), (int)nb);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < I4_STAGES - 1; ++i) issue(i);
+
+  // ---- Q fragments in the permuted head_dim order + per-row offsets ------------------------------
+  const int wrow = (KEY_WARPS == 1) ? warp * 16 : 0;
+  const int wkey = (KEY_WARPS == 1) ? 0 : warp * KPW;
+  uint32_t qa[8][4];
+  int tok_r[2];
+  float qsum[2], qoff[2];
+  {
+    const __half* qb = reinterpret_cast<const __half*>(p.q) + (long long)b * p.q_batch_stride;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int R = row0 + wrow + g + hf * 8;
+      const bool ok = R < rows_total;
+      const int tok = ok ? R / p.group : 0;
+      const int hq = kvh * p.group + (ok ? R % p.group : 0);
+      tok_r[hf] = ok ? tok : -1;
+      const __half* src = qb + (long long)tok * p.q_tok_stride + (long long)hq * kHeadDim + 32 * t4;
+      float s_all = 0.f, s_off = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        __half e[8];
+        if (ok) {
+          *reinterpret_cast<uint4*>(e) = *reinterpret_cast<const uint4*>(src + 8 * w);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = __float2half(0.f);
+        }
+        const __half sixteenth = __float2half(0.0625f);
+        // lo slots carry +1024, hi slots carry Q/16 against codes*16 (+1024)
+        const __half h0 = __hmul(e[0], sixteenth), h4 = __hmul(e[4], sixteenth);
+        const __half h2 = __hmul(e[2], sixteenth), h6 = __hmul(e[6], sixteenth);
+        qa[2 * w][hf] = Op::pack(__half2float(e[1]), __half2float(e[5]));          // k = 2t,2t+1   <- d+1, d+5
+        qa[2 * w][hf + 2] = Op::pack(__half2float(h0), __half2float(h4));           // k = 2t+8,+9   <- (d+0, d+4)/16
+        qa[2 * w + 1][hf] = Op::pack(__half2float(e[3]), __half2float(e[7]));      //               <- d+3, d+7
+        qa[2 * w + 1][hf + 2] = Op::pack(__half2float(h2), __half2float(h6));       //               <- (d+2, d+6)/16
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_all += __half2float(e[i]);
+        s_off += 1024.f * (__half2float(e[1]) + __half2float(e[5]) + __half2float(e[3]) + __half2float(e[7]) +
+                           __half2float(h0) + __half2float(h4) + __half2float(h2) + __half2float(h6));
+      }
+      s_all += __shfl_xor_sync(0xffffffffu, s_all, 1);
+      s_all += __shfl_xor_sync(0xffffffffu, s_all, 2);
+      s_off += __shfl_xor_sync(0xffffffffu, s_off, 1);
+      s_off += __shfl_xor_sync(0xffffffffu, s_off, 2);
+      qsum[hf] = s_all;
+      qoff[hf] = s_off;
+    }
+  }
+
+  float o[16][4];  // logical n-tile (blk, i): index blk*4+i, column n <-> head_dim 32 blk + 4 n + i
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};   // sum p
+  float ps_run[2] = {0.f, 0.f};  // sum fp16(p * s_v)   (offset removal)
+  float pz_run[2] = {0.f, 0.f};  // sum p * z_v
+  const int lrow = lane & 7, lmat = lane >> 3;
+
+  for (int i = 0; i < n_tiles; ++i) {
+    cp_async_wait<I4_STAGES - 2>();
+    __syncthreads();          // tile i landed for everyone; everyone is done with tile i-1
+    issue(i + I4_STAGES - 1); // refills the stage tile i-1 used
+    const uint8_t* st = smem + (i % I4_STAGES) * I4_STAGE_BYTES;
+    const uint32_t sK = smem_u32(st), sV = sK + I4_PACK_BYTES;
+    const __half* sKs = reinterpret_cast<const __half*>(st + 2 * I4_PACK_BYTES);
+    const __half* sKz = sKs + 64;
+    const __half* sVs = sKs + 128;
+    const __half* sVz = sKs + 192;
+    const long long j0 = tile_start(i);
+    const long long jend = tile_end(i);
+
+    // ---- S_raw = Q . codes(K) ----------------------------------------------------------------------
+    float sc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+      const int key = wkey + n * 8 + g;
+      const uint32_t addr = sK + key * 64 + ((t4 ^ ((key >> 1) & 3)) << 4);
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+      const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t x = ww[w], y = x >> 8;
+        Op::run(sc[n], qa[2 * w], lop_lo(x), lop_hi(x));
+        Op::run(sc[n], qa[2 * w + 1], lop_lo(y), lop_hi(y));
+      }
+    }
+    // ---- logits: s_j * (S_raw - qoff) + z_j * qsum, mask, online softmax ----------------------------
+    const long long kfirst = j0 + wkey;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int kc = wkey + n * 8 + 2 * t4;
+      const float2 ks = __half22float2(*reinterpret_cast<const __half2*>(sKs + kc));
+      const float2 kz = __half22float2(*reinterpret_cast<const __half2*>(sKz + kc));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int hf = e >> 1;
+        const float s_ = (e & 1) ? ks.y : ks.x, z_ = (e & 1) ? kz.y : kz.x;
+        float v = s_ * (sc[n][e] - qoff[hf]) + z_ * qsum[hf];
+        const long long j = kfirst + n * 8 + 2 * t4 + (e & 1);
+        const int tk = tok_r[hf];
+        bool vis = (tk >= 0) && (j < jend) && (j <= base + tk);
+        if (!is_full && i < nA) vis = vis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
+        sc[n][e] = vis ? v : -INFINITY;
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      mx[0] = fmaxf(mx[0], fmaxf(sc[n][0], sc[n][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sc[n][2], sc[n][3]));
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 1));
+      mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 2));
+    }
+    float alpha[2], msc[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float m_new = fmaxf(m_run[hf], mx[hf]);
+      msc[hf] = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+      alpha[hf] = (m_run[hf] == -INFINITY) ? 0.f : fast_exp2(m_run[hf] * p.scale_log2 - msc[hf]);
+      m_run[hf] = m_new;
+    }
+    float rs[2] = {0.f, 0.f}, rps[2] = {0.f, 0.f}, rpz[2] = {0.f, 0.f};
+    uint32_t pa[NT / 2][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int kc = wkey + n * 8 + 2 * t4;
+      const float2 vs = __half22float2(*reinterpret_cast<const __half2*>(sVs + kc));
+      const float2 vz = __half22float2(*reinterpret_cast<const __half2*>(sVz + kc));
+      const float p0 = fast_exp2(sc[n][0] * p.scale_log2 - msc[0]);
+      const float p1 = fast_exp2(sc[n][1] * p.scale_log2 - msc[0]);
+      const float p2 = fast_exp2(sc[n][2] * p.scale_log2 - msc[1]);
+      const float p3 = fast_exp2(sc[n][3] * p.scale_log2 - msc[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      rpz[0] += p0 * vz.x + p1 * vz.y;
+      rpz[1] += p2 * vz.x + p3 * vz.y;
+      const __half2 a = __floats2half2_rn(p0 * vs.x, p1 * vs.y);  // p' = p * s_v, rounded to fp16 like P
+      const __half2 c = __floats2half2_rn(p2 * vs.x, p3 * vs.y);
+      rps[0] += __low2float(a) + __high2float(a);
+      rps[1] += __low2float(c) + __high2float(c);
+      pa[n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&a);
+      pa[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&c);
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      l_run[hf] = l_run[hf] * alpha[hf] + rs[hf];
+      ps_run[hf] = ps_run[hf] * alpha[hf] + rps[hf];
+      pz_run[hf] = pz_run[hf] * alpha[hf] + rpz[hf];
+    }
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      o[d][0] *= alpha[0];
+      o[d][1] *= alpha[0];
+      o[d][2] *= alpha[1];
+      o[d][3] *= alpha[1];
+    }
+    // ---- O_raw += P' . codes(V): ldmatrix.trans on 16-bit units (4 codes of one key) ---------------
+#pragma unroll
+    for (int k2 = 0; k2 < NT / 2; ++k2) {
+#pragma unroll
+      for (int call = 0; call < 2; ++call) {
+        const int key = wkey + k2 * 16 + (lmat & 1) * 8 + lrow;
+        const int blk = 2 * call + (lmat >> 1);
+        const uint32_t addr = sV + key * 64 + ((blk ^ ((key >> 1) & 3)) << 4);
+        uint32_t r0, r1, r2, r3;  // (keys 0-7, blk) (keys 8-15, blk) (keys 0-7, blk+1) (keys 8-15, blk+1)
+        ldsm_x4_trans(r0, r1, r2, r3, addr);
+        const int nb = (2 * call) * 4;
+        Op::run(o[nb + 1], pa[k2], lop_lo(r0), lop_lo(r1));            // i = 1
+        Op::run(o[nb + 0], pa[k2], lop_hi(r0), lop_hi(r1));            // i = 0 (x16)
+        Op::run(o[nb + 3], pa[k2], lop_lo(r0 >> 8), lop_lo(r1 >> 8));  // i = 3
+        Op::run(o[nb + 2], pa[k2], lop_hi(r0 >> 8), lop_hi(r1 >> 8));  // i = 2 (x16)
+        Op::run(o[nb + 5], pa[k2], lop_lo(r2), lop_lo(r3));
+        Op::run(o[nb + 4], pa[k2], lop_hi(r2), lop_hi(r3));
+        Op::run(o[nb + 7], pa[k2], lop_lo(r2 >> 8), lop_lo(r3 >> 8));
+        Op::run(o[nb + 6], pa[k2], lop_hi(r2 >> 8), lop_hi(r3 >> 8));
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    l_run[hf] += __shfl_xor_sync(0xffffffffu, l_run[hf], 1);
+    l_run[hf] += __shfl_xor_sync(0xffffffffu, l_run[hf], 2);
+    ps_run[hf] += __shfl_xor_sync(0xffffffffu, ps_run[hf], 1);
+    ps_run[hf] += __shfl_xor_sync(0xffffffffu, ps_run[hf], 2);
+    pz_run[hf] += __shfl_xor_sync(0xffffffffu, pz_run[hf], 1);
+    pz_run[hf] += __shfl_xor_sync(0xffffffffu, pz_run[hf], 2);
+  }
+
+  // ---- true (un-normalised) O of this warp -> shared memory, in natural head_dim order -------------
+  __syncthreads();
+  float* sm_o = reinterpret_cast<float*>(smem);               // [ROWS][128] merged
+  float* sm_ml = reinterpret_cast<float*>(smem + 64 * 1024);  // [ROWS][2]
+  float* w_o = (KEY_WARPS == 4) ? reinterpret_cast<float*>(smem) + 16 * 128 : sm_o;  // [4][16][128] | [ROWS][128]
+  float* w_ml = (KEY_WARPS == 4) ? sm_ml + 64 : sm_ml;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int r = (KEY_WARPS == 4) ? (warp * 16 + g + hf * 8) : (wrow + g + hf * 8);
+    if (t4 == 0) {
+      w_ml[r * 2 + 0] = (m_run[hf] == -INFINITY) ? -INFINITY : m_run[hf] * p.scale_log2;
+      w_ml[r * 2 + 1] = l_run[hf];
+    }
+    const float off = 1024.f * ps_run[hf];
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const int blk = nt >> 2, ii = nt & 3;
+      const float mul = (ii & 1) ? 1.f : 0.0625f;  // hi-nibble columns carry codes * 16
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int d = 32 * blk + 4 * (2 * t4 + e) + ii;
+        w_o[r * 128 + d] = (o[nt][hf * 2 + e] - off) * mul + pz_run[hf];
+      }
+    }
+  }
+  __syncthreads();
+  if constexpr (KEY_WARPS == 4) {
+    for (int idx = tid; idx < 16 * 128; idx += I4_THREADS) {
+      const int r = idx >> 7, d = idx & 127;
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, w_ml[(w * 16 + r) * 2]);
+      float acc = 0.f, ll = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = w_ml[(w * 16 + r) * 2];
+        const float f = (mw == -INFINITY) ? 0.f : fast_exp2(mw - mm);
+        acc += f * w_o[(w * 16 + r) * 128 + d];
+        ll += f * w_ml[(w * 16 + r) * 2 + 1];
+      }
+      sm_o[r * 128 + d] = acc;
+      if (d == 0) {
+        sm_ml[r * 2] = mm;
+        sm_ml[r * 2 + 1] = ll;
+      }
+    }
+    __syncthreads();
+  }
+
+  __half* outb = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_batch_stride;
+  auto store_row_elem = [&](int r, int d, float v0, float v1) {
+    const int R = row0 + r;
+    const int tok = R / p.group;
+    const int hq = kvh * p.group + R % p.group;
+    __half* dst = outb + ((long long)tok * p.n_q_heads + hq) * kHeadDim + d;
+    *reinterpret_cast<uint32_t*>(dst) = Op::pack(v0, v1);
+  };
+  const int nsplit = is_full ? p.splits_full : 1;
+  if (nsplit == 1) {
+    for (int idx = tid; idx < rows_here * 64; idx += I4_THREADS) {
+      const int r = idx >> 6, d = (idx & 63) * 2;
+      const float l = sm_ml[r * 2 + 1];
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      store_row_elem(r, d, sm_o[r * 128 + d] * inv, sm_o[r * 128 + d + 1] * inv);
+    }
+    return;
+  }
+  // ---- split-KV publish + last-CTA merge (identical protocol to attn_mma.cu) ----------------------
+  const long long item = ((long long)b * p.n_full + kvh) * p.n_rb + rb;
+  float* wo = p.ws_o + (item * p.splits_full + split) * (long long)(ROWS * 128);
+  float* wml = p.ws_ml + (item * p.splits_full + split) * (long long)(ROWS * 2);
+  for (int idx = tid; idx < rows_here * 32; idx += I4_THREADS) {
+    const int r = idx >> 5, d4 = (idx & 31) * 4;
+    *reinterpret_cast<float4*>(&wo[r * 128 + d4]) = *reinterpret_cast<const float4*>(&sm_o[r * 128 + d4]);
+  }
+  if (tid < rows_here * 2) wml[tid] = sm_ml[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(&p.counters[item], 1);
+    s_is_last = (prev == p.splits_full - 1);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const float* po = p.ws_o + item * p.splits_full * (long long)(ROWS * 128);
+  const float* pml = p.ws_ml + item * p.splits_full * (long long)(ROWS * 2);
+  float* cm_o = reinterpret_cast<float*>(smem);
+  float* cm_ml = reinterpret_cast<float*>(smem + 80 * 1024);
+  for (int rg = 0; rg < rows_here; rg += 16) {
+    const int rg_n = min(16, rows_here - rg);
+    for (int rr = 0; rr < rg_n; ++rr) {
+      const int r = rg + rr;
+      float mm = -INFINITY, ll = 0.f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s0 = warp; s0 < p.splits_full; s0 += 16) {
+        float ms[4], ls[4];
+        float4 vs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s2 = s0 + 4 * u;
+          const bool ok = s2 < p.splits_full;
+          const int sc2 = ok ? s2 : s0;
+          ms[u] = ok ? __ldcg(&pml[(sc2 * ROWS + r) * 2]) : -INFINITY;
+          ls[u] = __ldcg(&pml[(sc2 * ROWS + r) * 2 + 1]);
+          vs[u] = __ldcg(reinterpret_cast<const float4*>(&po[((long long)sc2 * ROWS + r) * 128 + lane * 4]));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (ms[u] == -INFINITY) continue;
+          const float mn = fmaxf(mm, ms[u]);
+          const float fo = (mm == -INFINITY) ? 0.f : fast_exp2(mm - mn);
+          const float fn = fast_exp2(ms[u] - mn);
+          acc.x = acc.x * fo + vs[u].x * fn;
+          acc.y = acc.y * fo + vs[u].y * fn;
+          acc.z = acc.z * fo + vs[u].z * fn;
+          acc.w = acc.w * fo + vs[u].w * fn;
+          ll = ll * fo + ls[u] * fn;
+          mm = mn;
+        }
+      }
+      *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr) * 128 + lane * 4]) = acc;
+      if (lane == 0) {
+        cm_ml[(warp * 16 + rr) * 2] = mm;
+        cm_ml[(warp * 16 + rr) * 2 + 1] = ll;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < rg_n * 64; idx += I4_THREADS) {
+      const int rr = idx >> 6, d = (idx & 63) * 2;
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, cm_ml[(w * 16 + rr) * 2]);
+      float a0f = 0.f, a1f = 0.f, ll = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = cm_ml[(w * 16 + rr) * 2];
+        if (mw == -INFINITY) continue;
+        const float f = fast_exp2(mw - mm);
+        a0f += f * cm_o[(w * 16 + rr) * 128 + d];
+        a1f += f * cm_o[(w * 16 + rr) * 128 + d + 1];
+        ll += f * cm_ml[(w * 16 + rr) * 2 + 1];
+      }
+      const float inv = ll > 0.f ? 1.f / ll : 0.f;
+      store_row_elem(rg + rr, d, a0f * inv, a1f * inv);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) p.counters[item] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+int stage_offset(const duo_layer_desc& d);  // api.cu
+
+template <int KEY_WARPS>
+static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
+                     int q_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const duo_layer_desc& d = L->d;
+  constexpr int ROWS = 16 * (4 / KEY_WARPS);
+  I4Params p{};
+  p.q = q;
+  p.out = out;
+  p.q_tok_stride = q_row_stride;
+  p.q_batch_stride = q_row_stride * q_len;
+  const int n_q = (d.n_full + d.n_stream) * d.group;
+  p.out_batch_stride = (long long)q_len * n_q * kHeadDim;
+  p.q_len = q_len;
+  p.n_q_heads = n_q;
+  p.group = d.group;
+  p.n_full = d.n_full;
+  p.n_stream = d.n_stream;
+  p.batch = d.batch;
+  p.sink = d.sink;
+  p.recent = d.recent;
+  p.W = d.sink + d.recent;
+  p.stage_off = stage_offset(d);
+  p.full_len = st->full_len;
+  p.total = st->total;
+  p.lo = st->lo;
+  p.full_cap = d.full_cap;
+  p.ring_slots = (long long)p.stage_off + d.stage_cap;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int rows = d.group * q_len;
+  p.n_rb = (rows + ROWS - 1) / ROWS;
+  p.cache_scan = (int)std::min<long long>(p.W, st->total);
+  p.full_k = (const uint8_t*)d.full_k;
+  p.full_v = (const uint8_t*)d.full_v;
+  p.ring_k = (const uint8_t*)d.ring_k;
+  p.ring_v = (const uint8_t*)d.ring_v;
+  p.fks = (const __half*)d.full_k_scale;
+  p.fkz = (const __half*)d.full_k_zero;
+  p.fvs = (const __half*)d.full_v_scale;
+  p.fvz = (const __half*)d.full_v_zero;
+  p.rks = (const __half*)d.ring_k_scale;
+  p.rkz = (const __half*)d.ring_k_zero;
+  p.rvs = (const __half*)d.ring_v_scale;
+  p.rvz = (const __half*)d.ring_v_zero;
+
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int cached_dev = -1, cached_sms = 148;
+    if (cached_dev != dev) {
+      cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+      cached_dev = dev;
+    }
+    sm_count = cached_sms;
+  }
+  const long long nkeys = st->full_len + q_len;
+  int splits = 1;
+  if (d.n_full > 0) {
+    const int budget = 2 * sm_count;
+    const int base_ctas = d.batch * d.n_full * p.n_rb;
+    const int stream_ctas = d.batch * d.n_stream * p.n_rb;
+    int want = (budget - stream_ctas > 0 ? budget - stream_ctas : 1) / base_ctas;
+    if (want < 1) want = 1;
+    const long long max_by_len = (nkeys + 8 * I4_TILE - 1) / (8 * I4_TILE);  // >= 512 keys per split
+    splits = (int)std::min<long long>(want, std::max<long long>(1, max_by_len));
+    if (splits > 512) splits = 512;
+  }
+  long long kps = (nkeys + splits - 1) / splits;
+  kps = (kps + I4_TILE - 1) / I4_TILE * I4_TILE;
+  if (kps < I4_TILE) kps = I4_TILE;
+  splits = (int)((nkeys + kps - 1) / kps);
+  if (splits < 1) splits = 1;
+  p.splits_full = splits;
+  p.keys_per_split = (int)kps;
+  const long long items = (long long)d.batch * d.n_full * p.n_rb;
+  const size_t need_o = (size_t)items * splits * ROWS * 128 * 4;
+  const size_t need_ml = (size_t)items * splits * ROWS * 2 * 4;
+  const size_t need_cnt = (size_t)(items + 1) * 4;
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < need_o + need_ml + need_cnt + 1024)) {
+    set_error("duo_attention(int4): workspace too small (%zu < %zu)", workspace_bytes, need_o + need_ml + need_cnt + 1024);
+    return DUO_EWORKSPACE;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  p.counters = reinterpret_cast<int*>(ws);
+  const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
+  p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
+  p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
+  const int grid_x = d.n_full * p.n_rb * splits + d.n_stream * p.n_rb;
+  if (grid_x == 0) return DUO_OK;
+  auto kern = duo_attn_int4_kernel<KEY_WARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, I4_SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<dim3(grid_x, d.batch), I4_THREADS, I4_SMEM_BYTES, stream>>>(p);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+int launch_attn_int4(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
+                     int q_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (L->d.group * q_len <= 16)
+    return launch_i4<4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
+  return launch_i4<1>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
+}
+
 }  // namespace duo

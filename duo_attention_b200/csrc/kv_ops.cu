@@ -13,6 +13,8 @@
 
 namespace duo {
 
+int stage_offset(const duo_layer_desc& d);  // api.cu
+
 template <typename T>
 struct Cvt;
 template <>
@@ -75,7 +77,8 @@ struct RopeAppendParams {
   const void* sin;
   int rope_mode;
   int q_len, batch, n_q, n_kv, n_full, n_stream;
-  int W, ring_slots;  // sink+recent, sink+recent+stage_cap
+  int W, ring_slots;  // first staging slot, staging slot + stage_cap
+  int skip_q;
   long long full_cap, full_len;
   int kv_int4;
   void *full_k, *full_v, *ring_k, *ring_v;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const RopeAppendParams
   for (int i = 0; i < 4; ++i) xo[i] = Cvt<T>::to_f(xv.v[i]);
 
   if (is_q) {
-    if (p.rope_mode != DUO_ROPE_NONE) *reinterpret_cast<Vec4<T>*>(row + lane * 4) = xv;
+    if (p.rope_mode != DUO_ROPE_NONE && !p.skip_q) *reinterpret_cast<Vec4<T>*>(row + lane * 4) = xv;
     return;
   }
   const int h = is_k ? slot - p.n_q : slot - p.n_q - p.n_kv;
@@ -161,14 +164,15 @@ int launch_rope_append(const duo_layer* L, const duo_cache_state* st, void* qkv,
   p.row_stride = row_stride;
   p.cos = cos;
   p.sin = sin;
-  p.rope_mode = rope_mode;
+  p.rope_mode = rope_mode & 0xff;
+  p.skip_q = (rope_mode & DUO_ROPE_SKIP_Q) ? 1 : 0;
   p.q_len = q_len;
   p.batch = d.batch;
   p.n_kv = d.n_full + d.n_stream;
   p.n_q = p.n_kv * d.group;
   p.n_full = d.n_full;
   p.n_stream = d.n_stream;
-  p.W = d.sink + d.recent;
+  p.W = stage_offset(d);
   p.ring_slots = p.W + d.stage_cap;
   p.full_cap = d.full_cap;
   p.full_len = st->full_len;
@@ -205,7 +209,7 @@ struct CommitParams {
   __half *rks, *rkz, *rvs, *rvz;
   int row_bytes;  // 256 (16-bit) or 64 (int4)
   int kv_int4;
-  int batch, n_stream, ring_slots, W, sink, recent, q_len;
+  int batch, n_stream, ring_slots, W /* first staging slot */, sink, recent, q_len;
   long long total;
   int n_cand;      // candidate chunk rows per head: sinks first, then the tail
   int n_sink_new;  // chunk rows [0, n_sink_new) land in sink slots
@@ -265,7 +269,7 @@ int launch_stream_commit(const duo_layer* L, const duo_cache_state* st, int q_le
   p.row_bytes = p.kv_int4 ? 64 : 256;
   p.batch = d.batch;
   p.n_stream = d.n_stream;
-  p.W = d.sink + d.recent;
+  p.W = stage_offset(d);
   p.ring_slots = p.W + d.stage_cap;
   p.sink = d.sink;
   p.recent = d.recent;

@@ -118,10 +118,18 @@ class DuoKVCache:
     def W(self):
         return self.sink_size + self.recent_size
 
+    @property
+    def stage_off(self):
+        """First staging slot (duo_b200.h): right after the ring, 64-aligned for INT4 caches."""
+        return self.W if self.kv_format == "same" else (self.W + 63) // 64 * 64
+
     def _alloc_layer(self, l, full_cap, stage_cap):
         nf, ns = self.num_full_kv_head_list[l], self.num_streaming_kv_head_list[l]
         B, D, dev = self.batch_size, self.head_dim, self.device
-        slots = self.W + stage_cap
+        slots = self.stage_off + stage_cap
+        if self.kv_format == "int4":
+            slots = (slots + 7) // 8 * 8
+            full_cap = (full_cap + 63) // 64 * 64
         t = {}
         if self.kv_format == "same":
             for name, heads, rows in (("full_k", nf, full_cap), ("full_v", nf, full_cap),
@@ -146,14 +154,14 @@ class DuoKVCache:
             for suf in ("_scale", "_zero"):
                 key = name + suf
                 setattr(d, key, t[key].data_ptr() if key in t and t[key].numel() else None)
-        d.full_cap = self.full_cap_list[l]
+        d.full_cap = t["full_k"].shape[2]
         d.batch = self.batch_size
         d.n_full = self.num_full_kv_head_list[l]
         d.n_stream = self.num_streaming_kv_head_list[l]
         d.group = self.num_kv_groups
         d.head_dim = self.head_dim
         d.sink, d.recent = self.sink_size, self.recent_size
-        d.stage_cap = self.stage_cap_list[l]
+        d.stage_cap = t["ring_k"].shape[2] - self.stage_off
         d.dtype = _C.DT_BF16 if self.dtype == torch.bfloat16 else _C.DT_FP16
         d.kv_format = _C.KV_SAME if self.kv_format == "same" else _C.KV_INT4
         h = C.c_void_p()
@@ -200,6 +208,15 @@ class DuoKVCache:
         self.full_cap_list[l] = new_full
         self.stage_cap_list[l] = new_stage
         self._make_handle(l)
+
+    def _first_chunk_scratch(self, S):
+        sc = getattr(self, "_scratch", None)
+        if sc is None or sc.max_size < S:
+            sc = DuoKVCache(1, self.num_heads, self.num_kv_heads, self.head_dim, [self.num_kv_heads],
+                            self.batch_size, max(S, 64), self.sink_size, self.recent_size, self.dtype, self.device,
+                            stage_cap=1, kv_format="same")
+            self._scratch = sc
+        return sc
 
     def state(self, l) -> _C.CacheState:
         return _C.CacheState(self.kv_seq_len_list[l], self.total_list[l], self.lo_list[l])
@@ -264,11 +281,22 @@ class DuoKVCache:
         cp = cos.data_ptr() if cos is not None else None
         sp = sin.data_ptr() if sin is not None else None
         _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode, S, stream))
+        ah, ast = h, st
+        if self.kv_format == "int4" and st.full_len == 0 and st.total == 0:
+            # The reference attends the RAW fp16 K/V on the very first call and only later calls see the
+            # quantise->dequantise round trip (demo/w8a8kv4_llama.py:229-238 vs :239-274).  The chunk has just
+            # been quantised into the INT4 cache above; attention for this one call runs on an fp16 scratch layer
+            # (every head is plain causal on the first call, so all heads are "retrieval" there).
+            sc = self._first_chunk_scratch(S)
+            ah, ast = sc.handles[0], _C.CacheState(0, 0, sc.sink_size)
+            _C.check(lib.duo_rope_append(ah, C.byref(ast), qkv.data_ptr(), qkv.stride(1), cp, sp,
+                                         rope_mode | _C.ROPE_SKIP_Q, S, stream))
+            self.launch_count += 1
         fn = lib.duo_attention_mma if force_mma else lib.duo_attention
         if self.profile_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _C.check(fn(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), S, float(scale),
+        _C.check(fn(ah, C.byref(ast), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), S, float(scale),
                     self.workspace.data_ptr(), self.workspace.numel(), stream))
         if self.profile_events is not None:
             e1.record()

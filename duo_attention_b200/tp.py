@@ -87,3 +87,45 @@ def install_allreduce(model, group=None):
     model._duo_tp_group = group
     model._duo_tp = True
     return model
+
+
+@torch.no_grad()
+def shard_model(model, full_attention_heads, rank: int, world: int):
+    """Build this rank's head-parallel shard of an UNPATCHED HF Llama/Mistral model (real weights):
+    q/k/v rows and o_proj columns of the KV heads `plan_heads` assigns to `rank`, MLP gate/up rows and down columns
+    split evenly, embeddings / norms / lm_head replicated.  Returns ``(shard_model, local_mask)``; call
+    ``enable_duo_attention_eval(shard, local_mask, sink, recent)`` and ``install_allreduce(shard)`` on it.
+    The reference gets the same split from tensor_parallel's config (duo_attn/utils.py:132-195)."""
+    import copy
+
+    cfg = copy.deepcopy(model.config)
+    plan = plan_heads(full_attention_heads, world)
+    n_heads, n_kv = cfg.num_attention_heads, cfg.num_key_value_heads
+    head_dim = getattr(cfg, "head_dim", None) or cfg.hidden_size // n_heads
+    group = n_heads // n_kv
+    inter = cfg.intermediate_size
+    if inter % world:
+        raise ValueError(f"intermediate_size {inter} not divisible by {world}")
+    cfg.head_dim = head_dim
+    cfg.num_attention_heads = n_heads // world
+    cfg.num_key_value_heads = n_kv // world
+    cfg.intermediate_size = inter // world
+    shard = type(model)(cfg).to(next(model.parameters()).dtype)
+    shard.model.embed_tokens.weight.copy_(model.model.embed_tokens.weight)
+    shard.model.norm.weight.copy_(model.model.norm.weight)
+    shard.lm_head.weight.copy_(model.lm_head.weight)
+    lo, hi = rank * (inter // world), (rank + 1) * (inter // world)
+    for l, (src, dst) in enumerate(zip(model.model.layers, shard.model.layers)):
+        a, b = src.self_attn, dst.self_attn
+        wq, wk, wv, wo = shard_attention_weights(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.o_proj.weight,
+                                                 plan.owners[l][rank], group, head_dim)
+        b.q_proj.weight.copy_(wq)
+        b.k_proj.weight.copy_(wk)
+        b.v_proj.weight.copy_(wv)
+        b.o_proj.weight.copy_(wo)
+        dst.mlp.gate_proj.weight.copy_(src.mlp.gate_proj.weight[lo:hi])
+        dst.mlp.up_proj.weight.copy_(src.mlp.up_proj.weight[lo:hi])
+        dst.mlp.down_proj.weight.copy_(src.mlp.down_proj.weight[:, lo:hi])
+        dst.input_layernorm.weight.copy_(src.input_layernorm.weight)
+        dst.post_attention_layernorm.weight.copy_(src.post_attention_layernorm.weight)
+    return shard.eval(), plan.local_mask(rank)

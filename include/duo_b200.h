@@ -65,6 +65,8 @@ extern "C" {
                             round(round(x*cos) + round(rotate_half(x)*sin)) — bit-exact with torch */
 #define DUO_ROPE_FP32 2  /* cos/sin tables in fp32, fp32 math, one rounding (flashinfer semantics,
                             flashinfer_utils.py:29-59, with accurate trig)                  */
+#define DUO_ROPE_SKIP_Q 0x100 /* OR-able flag: leave q untouched (it was rotated by an earlier call on the
+                                 same buffer); k is still rotated on its way into the caches */
 
 /*
  * Geometry + buffers of ONE decoder layer's KV cache, head-major ("heads first, then tokens"):
@@ -78,6 +80,9 @@ extern "C" {
  *   KV heads are in the reference's reordered order: retrieval heads first
  *   (duo_attn/patch/utils.py:6-45); q-head i reads kv-head i / group.
  *
+ *   DUO_KV_INT4: the staging area starts at slot round_up(sink+recent, 64) instead of sink+recent (the
+ *   slots in between are unused) and full_cap / the ring slot count must be multiples of 8, so that every
+ *   64-key tile and its scale/zero rows are 16-byte aligned.
  *   DUO_KV_INT4: the k/v tensors hold head_dim/2 bytes per row (high nibble = even element,
  *   demo/quantize_int4.cu:33-40,137) and *_scale / *_zero are fp16 [batch][heads][slots]
  *   (group_size == head_dim == 128, demo/int4_kv.py:140).

@@ -268,6 +268,29 @@ def tuple_attention_core(q, k, v, past, n_full, groups, sink, recent, use_cache=
     return out, new_past
 
 
+def int4_roundtrip(x):
+    """quantise -> dequantise of an fp16 ``[..., 128]`` tensor with the reference's K1/K2 arithmetic
+    (what ``DuoAttentionStaticINT4KVCache.put`` + ``get`` hand to attention, demo/int4_kv.py:261-436)."""
+    from oracle import int4_oracle as Q
+
+    a = x.detach().cpu().numpy()
+    p, s, z = Q.quantize_int4(a)
+    return torch.from_numpy(Q.dequantize_int4(p, s, z)).to(x.dtype)
+
+
+def int4_attention_core(q, k, v, past, n_full, groups, sink, recent):
+    """demo/w8a8kv4_llama.py:215-278 after RoPE, fp16: the cache holds quantised K/V; the FIRST call attends
+    the raw k/v (:229-238), every later call attends the quantise->dequantise round trip of everything,
+    the new tokens included (:222-227,239-274).  Same tuple layout for ``past`` as tuple_attention_core,
+    holding the round-tripped values."""
+    kq, vq = int4_roundtrip(k), int4_roundtrip(v)
+    if past is None:
+        out = flash_attn_contract(q, k, v, causal=True)
+        _, new_past = tuple_attention_core(q, kq, vq, None, n_full, groups, sink, recent)
+        return out, new_past
+    return tuple_attention_core(q, kq, vq, past, n_full, groups, sink, recent)
+
+
 def tuple_forward(w: AttnWeights, hidden, cos, sin, past, sink, recent):
     """llama.py:146-306.  hidden ``[B,S,hidden]``; cos/sin ``[B,S,D]`` in hidden.dtype."""
     B, S, _ = hidden.shape
