@@ -292,7 +292,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from duo_attention_b200 import _C
+    from duo_attention_b200 import _C, ops
     from duo_attn.patch import DuoAttentionStaticKVCache
 
     _C.load()  # fail loudly if the CUDA extension is missing
@@ -335,7 +335,7 @@ def main():
         with torch.no_grad():
             prefill_once(False)  # warm-up (cuBLAS heuristics, TMA descriptors, allocator)
             barrier()
-            c0 = cache.launch_count
+            c0 = cache.launch_count + ops.LAUNCHES
             times = []
             for _ in range(args.prefill_reps):
                 cache.profile_events = []
@@ -350,7 +350,7 @@ def main():
                 times.append(max_over_ranks(e0.elapsed_time(e1)))
                 attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events)
             cache.profile_events = None
-            launches_prefill = cache.launch_count - c0
+            launches_prefill = cache.launch_count + ops.LAUNCHES - c0
         ms = min(times)
         fl = prefill_flops(mask, args.prefill_ctx, args.chunk)
         peaks = load_peaks()
@@ -388,7 +388,7 @@ def main():
             decode_step_resident()
         barrier()
         # --- value: inputs resident in HBM
-        c0 = cache.launch_count
+        c0 = cache.launch_count + ops.LAUNCHES
         cache.profile_events = []
         sampler.start()
         barrier()
@@ -402,7 +402,7 @@ def main():
         torch.cuda.nvtx.range_pop()
         clocks = sampler.stop()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
-        launches = cache.launch_count - c0
+        launches = cache.launch_count + ops.LAUNCHES - c0
         attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events) / args.steps
         n_attn = len(cache.profile_events) // args.steps
         cache.profile_events = None

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libduo_b200.so")
+LIB_PATH = os.environ.get("DUO_B200_LIB") or os.path.join(_HERE, "csrc", "libduo_b200.so")  # env: tuning builds
 
 DUO_OK, DUO_EINVAL, DUO_EOVERFLOW, DUO_ECUDA, DUO_EWORKSPACE = 0, -1, -2, -3, -4
 DT_BF16, DT_FP16 = 0, 1
@@ -21,8 +21,8 @@ DECODE_MAX_Q = 16
 # every symbol include/duo_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
     "duo_layer_create", "duo_layer_destroy", "duo_workspace_bytes", "duo_rope_append", "duo_attention",
-    "duo_attention_mma", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_last_error_string",
-    "duo_version",
+    "duo_attention_mma", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
+    "duo_last_error_string", "duo_version",
 ]
 
 
@@ -76,6 +76,10 @@ def load():
     lib.duo_quant_int4.restype = C.c_int
     lib.duo_dequant_int4.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.duo_dequant_int4.restype = C.c_int
+    lib.duo_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, i32, vp]
+    lib.duo_add_rmsnorm.restype = C.c_int
+    lib.duo_silu_mul.argtypes = [vp, vp, i64, i32, i32, vp]
+    lib.duo_silu_mul.restype = C.c_int
     lib.duo_last_error_string.argtypes = []
     lib.duo_last_error_string.restype = C.c_char_p
     lib.duo_version.argtypes = []

@@ -40,6 +40,10 @@ int launch_quant_int4(const void* in, long long in_row_stride, long long rows, v
 int launch_dequant_int4(const void* packed, const void* scale, const void* zero, long long rows, void* out,
                         cudaStream_t stream);
 
+int launch_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res,
+                       long long rows, int hidden, float eps, int dtype, cudaStream_t stream);
+int launch_silu_mul(const void* gate_up, void* out, long long rows, int inter, int dtype, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // TMA descriptors (cuTensorMapEncodeTiled fetched through the runtime: no -lcuda link dependency)
 // ---------------------------------------------------------------------------------------------
@@ -258,6 +262,25 @@ int duo_quant_int4(const void* in, int64_t in_row_stride, int64_t rows, void* pa
     return DUO_EINVAL;
   }
   return launch_quant_int4(in, in_row_stride, rows, packed, scale, zero, (cudaStream_t)stream);
+}
+
+int duo_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res, int64_t rows,
+                    int32_t hidden, float eps, int32_t dtype, void* stream) {
+  if (rows < 0 || hidden < 8 || hidden % 8 != 0 || hidden > 16384 || (rows > 0 && (!x || !weight || !out_norm)) ||
+      (dtype != DUO_DT_BF16 && dtype != DUO_DT_FP16)) {
+    set_error("duo_add_rmsnorm: bad argument");
+    return DUO_EINVAL;
+  }
+  return launch_add_rmsnorm(x, residual, weight, out_norm, out_res, rows, hidden, eps, dtype, (cudaStream_t)stream);
+}
+
+int duo_silu_mul(const void* gate_up, void* out, int64_t rows, int32_t inter, int32_t dtype, void* stream) {
+  if (rows < 0 || inter < 8 || inter % 8 != 0 || (rows > 0 && (!gate_up || !out)) ||
+      (dtype != DUO_DT_BF16 && dtype != DUO_DT_FP16)) {
+    set_error("duo_silu_mul: bad argument");
+    return DUO_EINVAL;
+  }
+  return launch_silu_mul(gate_up, out, rows, inter, dtype, (cudaStream_t)stream);
 }
 
 int duo_dequant_int4(const void* packed, const void* scale, const void* zero, int64_t rows, void* out, void* stream) {

@@ -260,23 +260,31 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
         Op::run(sc[n], qa[2 * w + 1], lop_lo(y), lop_hi(y));
       }
     }
-    // ---- logits: s_j * (S_raw - qoff) + z_j * qsum, mask, online softmax ----------------------------
+    // ---- logits: s_j * (S_raw - qoff) + z_j * qsum, mask (boundary tiles only), online softmax --------
     const long long kfirst = j0 + wkey;
+    const int tmin = (row0 + wrow) / p.group;
+    const bool need_mask = (kfirst + KPW > jend) || (kfirst + KPW - 1 > base + tmin) || (!is_full && i < nA);
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       const int kc = wkey + n * 8 + 2 * t4;
       const float2 ks = __half22float2(*reinterpret_cast<const __half2*>(sKs + kc));
       const float2 kz = __half22float2(*reinterpret_cast<const __half2*>(sKz + kc));
+      sc[n][0] = ks.x * (sc[n][0] - qoff[0]) + kz.x * qsum[0];
+      sc[n][1] = ks.y * (sc[n][1] - qoff[0]) + kz.y * qsum[0];
+      sc[n][2] = ks.x * (sc[n][2] - qoff[1]) + kz.x * qsum[1];
+      sc[n][3] = ks.y * (sc[n][3] - qoff[1]) + kz.y * qsum[1];
+    }
+    if (need_mask) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int hf = e >> 1;
-        const float s_ = (e & 1) ? ks.y : ks.x, z_ = (e & 1) ? kz.y : kz.x;
-        float v = s_ * (sc[n][e] - qoff[hf]) + z_ * qsum[hf];
-        const long long j = kfirst + n * 8 + 2 * t4 + (e & 1);
-        const int tk = tok_r[hf];
-        bool vis = (tk >= 0) && (j < jend) && (j <= base + tk);
-        if (!is_full && i < nA) vis = vis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
-        sc[n][e] = vis ? v : -INFINITY;
+      for (int n = 0; n < NT; ++n) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long j = kfirst + n * 8 + 2 * t4 + (e & 1);
+          const int tk = tok_r[e >> 1];
+          bool vis = (tk >= 0) && (j < jend) && (j <= base + tk);
+          if (!is_full && i < nA) vis = vis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
+          if (!vis) sc[n][e] = -INFINITY;
+        }
       }
     }
     float mx[2] = {-INFINITY, -INFINITY};
@@ -290,14 +298,31 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
       mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 1));
       mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 2));
     }
-    float alpha[2], msc[2];
+    // the running max rarely moves after the first tiles of a long context: rescale only when it does
+    const bool moved = __any_sync(0xffffffffu, (mx[0] > m_run[0]) || (mx[1] > m_run[1]));
+    float msc[2];
+    if (moved) {
+      float alpha[2];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const float m_new = fmaxf(m_run[hf], mx[hf]);
-      msc[hf] = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-      alpha[hf] = (m_run[hf] == -INFINITY) ? 0.f : fast_exp2(m_run[hf] * p.scale_log2 - msc[hf]);
-      m_run[hf] = m_new;
+      for (int hf = 0; hf < 2; ++hf) {
+        const float m_new = fmaxf(m_run[hf], mx[hf]);
+        const float msn = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+        alpha[hf] = (m_run[hf] == -INFINITY) ? 0.f : fast_exp2(m_run[hf] * p.scale_log2 - msn);
+        m_run[hf] = m_new;
+        l_run[hf] *= alpha[hf];
+        ps_run[hf] *= alpha[hf];
+        pz_run[hf] *= alpha[hf];
+      }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        o[d][0] *= alpha[0];
+        o[d][1] *= alpha[0];
+        o[d][2] *= alpha[1];
+        o[d][3] *= alpha[1];
+      }
     }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) msc[hf] = (m_run[hf] == -INFINITY) ? 0.f : m_run[hf] * p.scale_log2;
     float rs[2] = {0.f, 0.f}, rps[2] = {0.f, 0.f}, rpz[2] = {0.f, 0.f};
     uint32_t pa[NT / 2][4];
 #pragma unroll
@@ -322,16 +347,9 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
     }
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      l_run[hf] = l_run[hf] * alpha[hf] + rs[hf];
-      ps_run[hf] = ps_run[hf] * alpha[hf] + rps[hf];
-      pz_run[hf] = pz_run[hf] * alpha[hf] + rpz[hf];
-    }
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      o[d][0] *= alpha[0];
-      o[d][1] *= alpha[0];
-      o[d][2] *= alpha[1];
-      o[d][3] *= alpha[1];
+      l_run[hf] += rs[hf];
+      ps_run[hf] += rps[hf];
+      pz_run[hf] += rpz[hf];
     }
     // ---- O_raw += P' . codes(V): ldmatrix.trans on 16-bit units (4 codes of one key) ---------------
 #pragma unroll

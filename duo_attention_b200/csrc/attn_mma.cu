@@ -61,6 +61,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[STAGES];
   __shared__ int s_is_last;
+  __shared__ float s_wmax[2][4][16];  // per-tile row maxima of the 4 key-warps (short contexts only)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -230,6 +231,24 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     for (int hf = 0; hf < 2; ++hf) {
       mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 1));
       mx[hf] = fmaxf(mx[hf], __shfl_xor_sync(0xffffffffu, mx[hf], 2));
+    }
+    if constexpr (KEY_WARPS == 4) {
+      // Short contexts: let the 4 key-warps agree on one row max per tile, so P is rounded against the same
+      // reference a single-block kernel (FA2 / the oracle) uses; with only a few dozen keys the independent
+      // per-warp references would otherwise be the largest source of bf16 rounding noise.  Long contexts
+      // average that noise out and skip the extra barrier.
+      if (n_tiles <= 8) {
+        if (t4 == 0) {
+          s_wmax[i & 1][warp][g] = mx[0];
+          s_wmax[i & 1][warp][g + 8] = mx[1];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          mx[0] = fmaxf(mx[0], s_wmax[i & 1][w][g]);
+          mx[1] = fmaxf(mx[1], s_wmax[i & 1][w][g + 8]);
+        }
+      }
     }
     float alpha[2], msc[2];
 #pragma unroll

@@ -214,7 +214,7 @@ class DuoKVCache:
         if sc is None or sc.max_size < S:
             sc = DuoKVCache(1, self.num_heads, self.num_kv_heads, self.head_dim, [self.num_kv_heads],
                             self.batch_size, max(S, 64), self.sink_size, self.recent_size, self.dtype, self.device,
-                            stage_cap=1, kv_format="same")
+                            stage_cap=max(S, 64), kv_format="same")  # no streaming heads: staging costs nothing
             self._scratch = sc
         return sc
 

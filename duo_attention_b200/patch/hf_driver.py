@@ -48,6 +48,34 @@ def _fuse_qkv(attn):
         plan.bqkv = torch.cat([attn.q_proj.bias.data, attn.k_proj.bias.data, attn.v_proj.bias.data]).contiguous()
 
 
+def _fuse_gate_up(mlp):
+    """gate_proj | up_proj as one GEMM operand (views re-pointed, no extra memory)."""
+    w = torch.cat([mlp.gate_proj.weight.data, mlp.up_proj.weight.data], dim=0).contiguous()
+    n = mlp.gate_proj.weight.shape[0]
+    mlp.gate_proj.weight.data = w[:n]
+    mlp.up_proj.weight.data = w[n:]
+    mlp._duo_wgu = w
+
+
+def _mlp_forward(mlp, x):
+    """LlamaMLP / MistralMLP: down(silu(gate(x)) * up(x)) with one fused gate|up GEMM and one fused SiLU*mul."""
+    from .. import ops
+
+    w = getattr(mlp, "_duo_wgu", None)
+    if w is None or w.device != x.device:
+        _fuse_gate_up(mlp)
+        w = mlp._duo_wgu
+    return mlp.down_proj(ops.silu_mul(torch.nn.functional.linear(x, w)))
+
+
+def _fusable(layer):
+    m = layer.mlp
+    return (all(hasattr(m, n) for n in ("gate_proj", "up_proj", "down_proj"))
+            and m.gate_proj.bias is None and m.up_proj.bias is None
+            and type(getattr(m, "act_fn", None)).__name__ in ("SiLU", "SiLUActivation")
+            and hasattr(layer.input_layernorm, "variance_epsilon"))
+
+
 def duo_attention_layer_forward(attn, hidden_states, cos, sin, kv_cache: DuoKVCache, layer_idx: int,
                                 rope_mode: int = _C.ROPE_HF):
     """The hot path of one layer (replaces llama.py:146-306 / :309-434)."""
@@ -107,24 +135,47 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
         position_ids = position_ids.view(-1, S).long()[:1]
     cos, sin = base.rotary_emb(inputs_embeds, position_ids)  # [1, S, D] in the activation dtype
     cos, sin = cos[0].contiguous(), sin[0].contiguous()
-    h = inputs_embeds
+    h = inputs_embeds.contiguous() if input_ids is not None else inputs_embeds.clone()  # updated in place below
     tp_on = getattr(self, "_duo_tp", False)
     if tp_on:
         from ..tp import all_reduce_sum
-    for idx, layer in enumerate(base.layers):
-        res = h
-        x = layer.input_layernorm(h)
-        x = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
-        if tp_on:  # row-parallel o_proj partials -> one all-reduce per layer (NCCL over NVLink)
-            x = all_reduce_sum(x, self._duo_tp_group)
-        h = res + x
-        res = h
-        x = layer.post_attention_layernorm(h)
-        x = layer.mlp(x)
-        if tp_on:
-            x = all_reduce_sum(x, self._duo_tp_group)
-        h = res + x
-    h = base.norm(h[:, -1:, :])
+    layers = list(base.layers)
+    if h.is_cuda and h.shape[-1] % 8 == 0 and all(_fusable(l) for l in layers):
+        # fused glue: residual add + RMSNorm in one launch, gate|up in one GEMM, SiLU*up in one launch
+        from .. import ops
+
+        x, _ = ops.add_rmsnorm(h, None, layers[0].input_layernorm.weight, layers[0].input_layernorm.variance_epsilon)
+        for idx, layer in enumerate(layers):
+            a = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
+            if tp_on:  # row-parallel o_proj partials -> one all-reduce per layer (NCCL over NVLink)
+                a = all_reduce_sum(a, self._duo_tp_group)
+            ln2 = layer.post_attention_layernorm
+            x, h = ops.add_rmsnorm(a, h, ln2.weight, ln2.variance_epsilon)
+            m = _mlp_forward(layer.mlp, x)
+            if tp_on:
+                m = all_reduce_sum(m, self._duo_tp_group)
+            if idx + 1 < len(layers):
+                nxt = layers[idx + 1].input_layernorm
+                x, h = ops.add_rmsnorm(m, h, nxt.weight, nxt.variance_epsilon)
+            else:  # only the last position feeds the head (tuple_kv_cache.py:283-288)
+                x, _ = ops.add_rmsnorm(m[:, -1:, :].contiguous(), h[:, -1:, :].contiguous(), base.norm.weight,
+                                       base.norm.variance_epsilon)
+        h = x
+    else:
+        for idx, layer in enumerate(layers):
+            res = h
+            x = layer.input_layernorm(h)
+            x = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
+            if tp_on:
+                x = all_reduce_sum(x, self._duo_tp_group)
+            h = res + x
+            res = h
+            x = layer.post_attention_layernorm(h)
+            x = layer.mlp(x)
+            if tp_on:
+                x = all_reduce_sum(x, self._duo_tp_group)
+            h = res + x
+        h = base.norm(h[:, -1:, :])
     logits = self.lm_head(h)
     if getattr(self, "_duo_logits_float", True):
         logits = logits.float()

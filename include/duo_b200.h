@@ -183,6 +183,18 @@ DUO_API int duo_quant_int4(const void* in, int64_t in_row_stride, int64_t rows, 
 DUO_API int duo_dequant_int4(const void* packed, const void* scale, const void* zero, int64_t rows, void* out,
                      void* stream);
 
+/*
+ * Caller-side glue between the GEMMs of a decoder layer (the "next" row f3 of the scope table), HF arithmetic:
+ *   duo_add_rmsnorm : h = residual + x (if residual != NULL; h is written to out_res if out_res != NULL),
+ *                     out_norm = weight * T( h_fp32 * rsqrt(mean(h_fp32^2) + eps) )      [LlamaRMSNorm; replaces
+ *                     flashinfer_rmsnorm_forward, duo_attn/patch/flashinfer_utils.py:9-16]
+ *   duo_silu_mul    : out = T( T(silu(gate)) * up ) for gate_up = [rows][gate(inter) | up(inter)]
+ * rows x hidden / rows x inter, contiguous, hidden and inter multiples of 8.
+ */
+DUO_API int duo_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res,
+                            int64_t rows, int32_t hidden, float eps, int32_t dtype, void* stream);
+DUO_API int duo_silu_mul(const void* gate_up, void* out, int64_t rows, int32_t inter, int32_t dtype, void* stream);
+
 DUO_API const char* duo_last_error_string(void);
 DUO_API int duo_version(void);
 

@@ -31,7 +31,8 @@ def assert_parity(got: torch.Tensor, ref: torch.Tensor, what: str = ""):
     viol = err > (ATOL + RTOL * ref.abs())
     frac = viol.float().mean().item()
     hard = err > (HARD_ATOL + HARD_RTOL * ref.abs())
-    if frac > MAX_VIOLATION_FRACTION or hard.any():
+    allowed = max(MAX_VIOLATION_FRACTION, 8.0 / viol.numel())  # small tensors: a handful of elements
+    if frac > allowed or hard.any():
         idx = tuple(int(i) for i in torch.nonzero(err == err.max())[0])
         raise AssertionError(
             f"{what}: {frac:.2e} of elements outside rtol={RTOL}/atol={ATOL} (allowed {MAX_VIOLATION_FRACTION:.0e}), "
