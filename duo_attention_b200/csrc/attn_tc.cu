@@ -13,8 +13,9 @@
 //               softmax warpgroup i is busy (ping-pong); completion signalled with tcgen05.commit
 //   warp 2      TMEM allocator (512 columns: S0 | S1 | O0 | O1; P_i aliases the first 64 columns of S_i)
 //   warps 4-7   softmax warpgroup 0: one thread per query row of tile 0 — tcgen05.ld S row, mask,
-//   warps 8-11  softmax warpgroup 1   online softmax with the exact running max (O in TMEM is rescaled only in the
-//               tiles where a row max grows), P -> bf16 -> tcgen05.st, final O/l -> global
+//   warps 8-11  softmax warpgroup 1   online softmax with a LAZY reference (O in TMEM is rescaled only when a row max
+//               outgrows the reference by 2^8) and SPECULATIVE exponentials (start before the tile max is
+//               known), P -> bf16 -> tcgen05.st, final O/l -> global
 //
 // Masks: retrieval heads use bottom-right causal over [cache | chunk]; streaming heads attend the
 // live sink/ring slots (validity table in smem) plus the staged chunk causally — see duo_b200.h.
@@ -339,6 +340,60 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const long long jend = (j < nA) ? a1 : b1;
       mbar_wait(&bars.s_full[slot], j & 1);
       tc_fence_after();
+      const bool cache_seg = (!is_full) && (j < nA);
+      const bool need_mask = cache_seg || (j0 + TC_TILE > jend) || (j0 + TC_TILE - 1 > base + slot_tok0[slot]);
+      // ---- fast path (the common tile: no mask, every row of the warp already has a finite reference) -------
+      // SPECULATE that no row max of this tile outgrows the current reference by more than 2^8: the exponentials
+      // are then independent of the tile's own max, so they start as soon as the first 32 S columns are in
+      // registers and overlap the remaining TMEM loads instead of waiting for load-all + max-reduce.  P may be
+      // as large as 2^8 (lazy reference, exact in the final O/l); a mis-speculation (rare after the first tile)
+      // falls through to the generic path below, which recomputes from the still intact S.
+      if (!need_mask && __all_sync(0xffffffffu, m_ref != -INFINITY)) {
+        const float mref_c = m_ref * c;
+        uint32_t pk[64];
+        uint32_t ra[32], rb[32];
+        float mx = -INFINITY, rs = 0.f;
+        auto consume = [&](const uint32_t (&r)[32], int ch) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
+            mx = fmaxf(mx, fmaxf(v0, v1));
+            const float p0 = fast_exp2(v0 * c - mref_c);
+            const float p1 = fast_exp2(v1 * c - mref_c);
+            rs += p0 + p1;
+            pk[ch * 16 + i] = TcType<T>::pack(p0, p1);
+          }
+        };
+        tmem_ld32(tS, ra);
+        tmem_wait_ld();
+        tmem_ld32(tS + 32, rb);
+        consume(ra, 0);
+        tmem_wait_ld();
+        tmem_ld32(tS + 64, ra);
+        consume(rb, 1);
+        tmem_wait_ld();
+        tmem_ld32(tS + 96, rb);
+        consume(ra, 2);
+        tmem_wait_ld();
+        consume(rb, 3);
+        const bool outgrown = (mx - m_ref) * c > 8.0f;
+        if (!__any_sync(0xffffffffu, outgrown)) {
+          uint32_t half0[32], half1[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            half0[i] = pk[i];
+            half1[i] = pk[32 + i];
+          }
+          tmem_st32(tS, half0);
+          tmem_st32(tS + 32, half1);
+          l_run += rs;
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bars.p_full[slot]);
+          continue;
+        }
+      }
+      // ---- generic path: masked tiles, first tile, mis-speculated tiles -----------------------------------
       float sv[128];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -348,8 +403,6 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         for (int i = 0; i < 32; ++i) sv[ch * 32 + i] = __uint_as_float(r[i]);
       }
       tmem_wait_ld();
-      const bool cache_seg = (!is_full) && (j < nA);
-      const bool need_mask = cache_seg || (j0 + TC_TILE > jend) || (j0 + TC_TILE - 1 > base + slot_tok0[slot]);
       if (need_mask) {
 #pragma unroll
         for (int i = 0; i < 128; ++i) {
@@ -362,10 +415,8 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       float mx = sv[0];
 #pragma unroll
       for (int i = 1; i < 128; ++i) mx = fmaxf(mx, sv[i]);
-      // FA2 arithmetic: the reference is the exact running row max (P <= 1, the dominant P is exactly 1), so O
-      // is rescaled whenever a row max of this warp grows.  After the first few dozen tiles that is rare
-      // (a new maximum appears in tile j with probability ~1/j), so the TMEM round trip costs a few percent.
-      bool grow = mx > m_ref;
+      // lazy reference: only move it when the row max outgrows it by more than 2^8 (or it is still -inf)
+      bool grow = (mx > m_ref) && ((m_ref == -INFINITY) || ((mx - m_ref) * c > 8.0f));
       const bool any_grow = __any_sync(0xffffffffu, grow && (j > 0));
       if (j == 0) {
         if (grow) m_ref = mx;
