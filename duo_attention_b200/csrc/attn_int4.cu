@@ -24,13 +24,18 @@
 
 namespace duo {
 
-constexpr int I4_TILE = 64;
-constexpr int I4_STAGES = 4;
-constexpr int I4_PACK_BYTES = I4_TILE * 64;                   // one packed K or V tile
-constexpr int I4_STAGE_BYTES = 2 * I4_PACK_BYTES + 4 * 128;   // + k_scale, k_zero, v_scale, v_zero
+// keys per pipeline stage: 128 for the decode variant (4 key-warps x 32 keys: halves the per-tile fixed cost of
+// the ALU-bound loop), 64 for the 64-row chunk variant
+template <int KEY_WARPS>
+struct I4Cfg {
+  static constexpr int TILE = KEY_WARPS == 4 ? 128 : 64;
+  static constexpr int STAGES = KEY_WARPS == 4 ? 3 : 4;
+  static constexpr int PACK_BYTES = TILE * 64;                  // one packed K or V tile
+  static constexpr int STAGE_BYTES = 2 * PACK_BYTES + 4 * TILE * 2;  // + k_scale, k_zero, v_scale, v_zero
+};
 constexpr int I4_THREADS = 128;
-constexpr int I4_MERGE_BYTES = 96 * 1024;                     // smem the split-KV merge needs (see attn_mma.cu)
-constexpr int I4_SMEM_BYTES = (I4_STAGES * I4_STAGE_BYTES > I4_MERGE_BYTES ? I4_STAGES * I4_STAGE_BYTES : I4_MERGE_BYTES) + 128;
+constexpr int I4_MERGE_BYTES = 96 * 1024;  // smem the split-KV merge needs (see attn_mma.cu); >= every pipeline
+constexpr int I4_SMEM_BYTES = I4_MERGE_BYTES + 128;
 
 struct I4Params {
   const void* q;
@@ -68,6 +73,10 @@ template <int KEY_WARPS>
 __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Params p) {
   constexpr int ROW_WARPS = 4 / KEY_WARPS;
   constexpr int ROWS = 16 * ROW_WARPS;
+  constexpr int I4_TILE = I4Cfg<KEY_WARPS>::TILE;
+  constexpr int I4_STAGES = I4Cfg<KEY_WARPS>::STAGES;
+  constexpr int I4_PACK_BYTES = I4Cfg<KEY_WARPS>::PACK_BYTES;
+  constexpr int I4_STAGE_BYTES = I4Cfg<KEY_WARPS>::STAGE_BYTES;
   constexpr int KPW = I4_TILE / KEY_WARPS;
   constexpr int NT = KPW / 8;
   using Op = MmaOp<__half>;
@@ -150,8 +159,8 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
       const long long lim = min(tile_end(i), slots);  // rows >= lim are not read (zero-filled)
       const uint32_t sbase = smem_u32(smem + (i % I4_STAGES) * I4_STAGE_BYTES);
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int chunk = tid + it * I4_THREADS;  // 0..255: row = chunk/4, c = chunk%4
+      for (int it = 0; it < I4_TILE * 4 / I4_THREADS; ++it) {
+        const int chunk = tid + it * I4_THREADS;  // row = chunk/4, c = chunk%4
         const int r = chunk >> 2, c = chunk & 3;
         const bool ok = (j0 + r) < lim;
         const long long srow = ok ? (j0 + r) : 0;
@@ -159,13 +168,14 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
         cp_async16(sbase + doff, gk + srow * 64 + c * 16, ok ? 16 : 0);
         cp_async16(sbase + I4_PACK_BYTES + doff, gv + srow * 64 + c * 16, ok ? 16 : 0);
       }
-      if (tid < 32) {
-        const int arr = tid >> 3, qd = tid & 7;  // 4 arrays x 8 chunks of 8 rows
+      if (tid < I4_TILE / 2) {
+        constexpr int CPA = I4_TILE / 8;          // 16-byte chunks per scale/zero array
+        const int arr = tid / CPA, qd = tid % CPA;  // 4 arrays x CPA chunks of 8 rows
         const __half* src = arr == 0 ? gks : arr == 1 ? gkz : arr == 2 ? gvs : gvz;
         const long long r0 = j0 + qd * 8;
         long long nb = (lim - r0) * 2;
         nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-        cp_async16(sbase + 2 * I4_PACK_BYTES + arr * 128 + qd * 16, src + (nb > 0 ? r0 : 0), (int)nb);
+        cp_async16(sbase + 2 * I4_PACK_BYTES + arr * (I4_TILE * 2) + qd * 16, src + (nb > 0 ? r0 : 0), (int)nb);
       }
     }
     cp_async_commit();
@@ -237,9 +247,9 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
     const uint8_t* st = smem + (i % I4_STAGES) * I4_STAGE_BYTES;
     const uint32_t sK = smem_u32(st), sV = sK + I4_PACK_BYTES;
     const __half* sKs = reinterpret_cast<const __half*>(st + 2 * I4_PACK_BYTES);
-    const __half* sKz = sKs + 64;
-    const __half* sVs = sKs + 128;
-    const __half* sVz = sKs + 192;
+    const __half* sKz = sKs + I4_TILE;
+    const __half* sVs = sKs + 2 * I4_TILE;
+    const __half* sVz = sKs + 3 * I4_TILE;
     const long long j0 = tile_start(i);
     const long long jend = tile_end(i);
 
@@ -544,6 +554,7 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
                      int q_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const duo_layer_desc& d = L->d;
   constexpr int ROWS = 16 * (4 / KEY_WARPS);
+  constexpr int I4_TILE = I4Cfg<KEY_WARPS>::TILE;
   I4Params p{};
   p.q = q;
   p.out = out;
