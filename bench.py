@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fa2", action="store_true", help="skip the same-box FlashAttention-2 micro-comparison")
+    ap.add_argument("--no-graph", action="store_true", help="drive decode eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -371,26 +372,51 @@ def main():
     tok_dev = torch.randint(0, vocab, (1, 1), generator=gcpu).to(dev)
     tok_host = torch.randint(0, vocab, (1, 1), generator=gcpu).pin_memory()
 
+    graph = None
+
     def decode_step_resident():
-        out = model(input_ids=tok_dev, past_key_values=cache, use_cache=True)
+        if graph is not None:
+            graph.step(tok_dev)
+        else:
+            model(input_ids=tok_dev, past_key_values=cache, use_cache=True)
         cache.evict_last(1)
-        return out
+        if graph is not None:
+            graph.resync()
 
     def decode_step_e2e():
-        out = model(input_ids=tok_host.to(dev, non_blocking=True), past_key_values=cache, use_cache=True)
-        nxt = int(out.logits[:, -1, :].argmax(-1).item())  # D2H of the step's result
+        if graph is not None:
+            logits = graph.step(tok_host)  # pinned host token -> device inside the step
+        else:
+            logits = model(input_ids=tok_host.to(dev, non_blocking=True), past_key_values=cache, use_cache=True).logits
+        nxt = int(logits[:, -1, :].argmax(-1).item())  # D2H of the step's result
         cache.evict_last(1)
+        if graph is not None:
+            graph.resync()
         return nxt
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # 200 ms period: spans warm-up, the timed decode steps and the e2e steps
     with torch.no_grad():
+        # --- kernel timing pass (eager, CUDA events around every duo_attention launch on its stream) -> roofline
+        for _ in range(max(3, args.warmup)):
+            decode_step_resident()
+        barrier()
+        cache.profile_events = []
+        for _ in range(args.steps):
+            decode_step_resident()
+        torch.cuda.synchronize()
+        attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events) / args.steps
+        n_attn = len(cache.profile_events) // args.steps
+        cache.profile_events = None
+        if not args.no_graph:
+            from duo_attention_b200.graph import DuoDecodeGraph
+
+            graph = DuoDecodeGraph(model, cache)
         for _ in range(max(3, args.warmup)):
             decode_step_resident()
         barrier()
         # --- value: inputs resident in HBM
         c0 = cache.launch_count + ops.LAUNCHES
-        cache.profile_events = []
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed_decode")
@@ -402,9 +428,6 @@ def main():
         torch.cuda.nvtx.range_pop()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = cache.launch_count + ops.LAUNCHES - c0
-        attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events) / args.steps
-        n_attn = len(cache.profile_events) // args.steps
-        cache.profile_events = None
         # --- e2e: host token in, host token out, every step
         for _ in range(2):
             decode_step_e2e()
@@ -419,6 +442,8 @@ def main():
             decode_step_resident()
         torch.cuda.synchronize()
     clocks = sampler.stop()
+    if graph is not None:  # a replayed step launches the same kernels as the captured one
+        launches = args.steps * per_step_launches(cache, ops, model, tok_dev)
 
     ms_step = ms_total / args.steps
     peaks = load_peaks()
@@ -432,7 +457,7 @@ def main():
         "config": workload_config(args, sparsity),
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": 8,
                 "d2h_bytes_per_step": 8},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "decode_driver": "eager" if args.no_graph else "cuda-graph replay (DuoDecodeGraph)",
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None,
@@ -565,6 +590,20 @@ def fa2_same_box(dev, ctx, chunk, prefill_ctx):
     del cache
     torch.cuda.empty_cache()
     return res
+
+
+def per_step_launches(cache, ops, model, tok_dev):
+    """Kernels of OUR library in one decode step (counted on one eager step)."""
+    import torch
+
+    c0 = cache.launch_count + ops.LAUNCHES
+    ds, cache.dev_state = cache.dev_state, None  # eager step without touching the graph's device state
+    with torch.no_grad():
+        model(input_ids=tok_dev, past_key_values=cache, use_cache=True)
+    cache.evict_last(1)
+    cache.dev_state = ds
+    cache.sync_device_state()
+    return cache.launch_count + ops.LAUNCHES - c0
 
 
 def ms_step_guess(ms_total, steps):

@@ -21,7 +21,7 @@ DECODE_MAX_Q = 16
 # every symbol include/duo_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
     "duo_layer_create", "duo_layer_destroy", "duo_workspace_bytes", "duo_rope_append", "duo_attention",
-    "duo_attention_mma", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
+    "duo_attention_mma", "duo_state_advance", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
     "duo_last_error_string", "duo_version",
 ]
 
@@ -40,7 +40,7 @@ class LayerDesc(C.Structure):
 
 
 class CacheState(C.Structure):
-    _fields_ = [("full_len", C.c_int64), ("total", C.c_int64), ("lo", C.c_int64)]
+    _fields_ = [("full_len", C.c_int64), ("total", C.c_int64), ("lo", C.c_int64), ("device_state", C.c_void_p)]
 
 
 _lib = None
@@ -70,6 +70,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = [vp, C.POINTER(CacheState), vp, i64, vp, i32, f32, vp, sz, vp]
         fn.restype = C.c_int
+    lib.duo_state_advance.argtypes = [vp, i32, i32, i32, vp]
+    lib.duo_state_advance.restype = C.c_int
     lib.duo_stream_commit.argtypes = [vp, C.POINTER(CacheState), i32, vp]
     lib.duo_stream_commit.restype = C.c_int
     lib.duo_quant_int4.argtypes = [vp, i64, i64, vp, vp, vp, vp]

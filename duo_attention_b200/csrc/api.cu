@@ -37,6 +37,7 @@ int launch_rope_append(const duo_layer* L, const duo_cache_state* st, void* qkv,
 int launch_stream_commit(const duo_layer* L, const duo_cache_state* st, int q_len, cudaStream_t stream);
 int launch_quant_int4(const void* in, long long in_row_stride, long long rows, void* packed, void* scale, void* zero,
                       cudaStream_t stream);
+int launch_state_advance(long long* st, int n, int sink, int recent, cudaStream_t stream);
 int launch_dequant_int4(const void* packed, const void* scale, const void* zero, long long rows, void* out,
                         cudaStream_t stream);
 
@@ -230,6 +231,10 @@ int duo_attention(const duo_layer* layer, const duo_cache_state* st, const void*
   if (layer->d.kv_format == DUO_KV_INT4)
     return launch_attn_int4(layer, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes,
                             (cudaStream_t)stream);
+  if (st->device_state && q_len > DUO_DECODE_MAX_Q) {
+    set_error("duo_attention: device_state is only supported for chunks of <= %d tokens", DUO_DECODE_MAX_Q);
+    return DUO_EINVAL;
+  }
   if (tc_prefill_supported(layer, st, q_len))
     return launch_attn_tc(layer, st, q, q_row_stride, out, q_len, scale, (cudaStream_t)stream);
   return launch_attn_mma(layer, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes,
@@ -247,6 +252,14 @@ int duo_attention_mma(const duo_layer* layer, const duo_cache_state* st, const v
   }
   return launch_attn_mma(layer, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes,
                          (cudaStream_t)stream);
+}
+
+int duo_state_advance(int64_t* device_state, int32_t n, int32_t sink, int32_t recent, void* stream) {
+  if (!device_state || n < 0 || recent < 1 || sink < 0) {
+    set_error("duo_state_advance: bad argument");
+    return DUO_EINVAL;
+  }
+  return launch_state_advance(reinterpret_cast<long long*>(device_state), n, sink, recent, (cudaStream_t)stream);
 }
 
 int duo_stream_commit(const duo_layer* layer, const duo_cache_state* st, int32_t q_len, void* stream) {

@@ -44,6 +44,7 @@ struct I4Params {
   int q_len, n_q_heads, group, n_full, n_stream, batch;
   int sink, recent, W, stage_off;
   long long full_len, total, lo;
+  const long long* dstate;
   long long full_cap, ring_slots;
   float scale_log2;
   int splits_full, keys_per_split, n_rb, cache_scan;
@@ -70,7 +71,19 @@ __device__ __forceinline__ uint32_t lop_hi(uint32_t w) {  // half2(1024 + 16 nib
 }
 
 template <int KEY_WARPS>
-__global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Params p) {
+__global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Params pin) {
+  I4Params p = pin;
+  if (pin.dstate) {  // occupancy lives in device memory (CUDA-graph replay)
+    p.full_len = pin.dstate[0];
+    p.total = pin.dstate[1];
+    p.lo = pin.dstate[2];
+    const long long nk = p.full_len + p.q_len;
+    constexpr int TL = I4Cfg<KEY_WARPS>::TILE;
+    long long kps = (nk + p.splits_full - 1) / p.splits_full;
+    kps = (kps + TL - 1) / TL * TL;
+    p.keys_per_split = (int)(kps < TL ? TL : kps);
+    p.cache_scan = (int)(p.total < p.W ? p.total : p.W);
+  }
   constexpr int ROW_WARPS = 4 / KEY_WARPS;
   constexpr int ROWS = 16 * ROW_WARPS;
   constexpr int I4_TILE = I4Cfg<KEY_WARPS>::TILE;
@@ -575,6 +588,7 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
   p.full_len = st->full_len;
   p.total = st->total;
   p.lo = st->lo;
+  p.dstate = reinterpret_cast<const long long*>(st->device_state);
   p.full_cap = d.full_cap;
   p.ring_slots = (long long)p.stage_off + d.stage_cap;
   p.scale_log2 = scale * 1.4426950408889634f;

@@ -36,6 +36,7 @@ struct AttnParams {
   int q_len, n_q_heads, group, n_full, n_stream, batch;
   int sink, recent, W;
   long long full_len, total, lo;
+  const long long* dstate;   // optional device copy of {full_len,total,lo} (CUDA-graph replay)
   float scale_log2;
   int splits_full;       // key splits for retrieval heads
   int keys_per_split;    // multiple of TILE
@@ -50,7 +51,18 @@ template <typename T, int KEY_WARPS>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
 duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_constant__ CUtensorMap map_fv,
                     const __grid_constant__ CUtensorMap map_rk, const __grid_constant__ CUtensorMap map_rv,
-                    const AttnParams p) {
+                    const AttnParams pin) {
+  AttnParams p = pin;
+  if (pin.dstate) {  // occupancy lives in device memory: recompute everything that depends on it
+    p.full_len = pin.dstate[0];
+    p.total = pin.dstate[1];
+    p.lo = pin.dstate[2];
+    const long long nk = p.full_len + p.q_len;
+    long long kps = (nk + p.splits_full - 1) / p.splits_full;
+    kps = (kps + TILE - 1) / TILE * TILE;
+    p.keys_per_split = (int)(kps < TILE ? TILE : kps);
+    p.cache_scan = (int)(p.total < p.W ? p.total : p.W);
+  }
   constexpr int ROW_WARPS = 4 / KEY_WARPS;
   constexpr int ROWS = 16 * ROW_WARPS;
   constexpr int KPW = TILE / KEY_WARPS;  // keys per warp per tile
@@ -510,6 +522,7 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   p.full_len = st->full_len;
   p.total = st->total;
   p.lo = st->lo;
+  p.dstate = reinterpret_cast<const long long*>(st->device_state);
   p.scale_log2 = scale * 1.4426950408889634f;
   const int rows = d.group * q_len;
   p.n_rb = (rows + ROWS - 1) / ROWS;

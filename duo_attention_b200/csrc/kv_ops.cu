@@ -80,6 +80,7 @@ struct RopeAppendParams {
   int W, ring_slots;  // first staging slot, staging slot + stage_cap
   int skip_q;
   long long full_cap, full_len;
+  const long long* dstate;
   int kv_int4;
   void *full_k, *full_v, *ring_k, *ring_v;
   __half *fks, *fkz, *fvs, *fvz, *rks, *rkz, *rvs, *rvz;
@@ -142,8 +143,9 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const RopeAppendParams
   const int h = is_k ? slot - p.n_q : slot - p.n_q - p.n_kv;
   const bool full = h < p.n_full;
   long long dst_row;  // row index inside the destination tensor
+  const long long full_len = p.dstate ? p.dstate[0] : p.full_len;
   if (full)
-    dst_row = ((long long)b * p.n_full + h) * p.full_cap + p.full_len + t;
+    dst_row = ((long long)b * p.n_full + h) * p.full_cap + full_len + t;
   else
     dst_row = ((long long)b * p.n_stream + (h - p.n_full)) * p.ring_slots + p.W + t;
   void* base = full ? (is_k ? p.full_k : p.full_v) : (is_k ? p.ring_k : p.ring_v);
@@ -176,6 +178,7 @@ int launch_rope_append(const duo_layer* L, const duo_cache_state* st, void* qkv,
   p.ring_slots = p.W + d.stage_cap;
   p.full_cap = d.full_cap;
   p.full_len = st->full_len;
+  p.dstate = reinterpret_cast<const long long*>(st->device_state);
   p.kv_int4 = d.kv_format == DUO_KV_INT4;
   p.full_k = d.full_k;
   p.full_v = d.full_v;
@@ -211,6 +214,7 @@ struct CommitParams {
   int kv_int4;
   int batch, n_stream, ring_slots, W /* first staging slot */, sink, recent, q_len;
   long long total;
+  const long long* dstate;  // when set: total is read from device memory and all q_len rows are candidates
   int n_cand;      // candidate chunk rows per head: sinks first, then the tail
   int n_sink_new;  // chunk rows [0, n_sink_new) land in sink slots
   int tail_start;  // chunk rows [tail_start, q_len) land in the ring
@@ -226,12 +230,18 @@ __global__ void __launch_bounds__(256) stream_commit_kernel(const CommitParams p
   const int c = (int)(x % p.n_cand);
   const long long bh = x / p.n_cand;
   int i;
-  if (c < p.n_sink_new)
+  long long total = p.total;
+  if (p.dstate) {
+    total = p.dstate[1];
+    i = c;  // every chunk row is a candidate; keep sinks and the last `recent` rows
+    if (!(total + i < p.sink || i >= p.q_len - p.recent)) return;
+  } else if (c < p.n_sink_new) {
     i = c;
-  else
+  } else {
     i = p.tail_start + (c - p.n_sink_new);
+  }
   if (i >= p.q_len) return;
-  const long long pos = p.total + i;
+  const long long pos = total + i;
   int slot;
   if (pos < p.sink)
     slot = (int)pos;
@@ -284,6 +294,8 @@ int launch_stream_commit(const duo_layer* L, const duo_cache_state* st, int q_le
   p.n_sink_new = (int)n_sink_new;
   p.tail_start = tail_start;
   p.n_cand = (int)n_sink_new + (q_len - tail_start);
+  p.dstate = reinterpret_cast<const long long*>(st->device_state);
+  if (p.dstate) p.n_cand = q_len;
   if (p.n_cand <= 0) return DUO_OK;
   const long long rows = (long long)d.batch * d.n_stream * p.n_cand * 2;
   const long long blocks = (rows + 7) / 8;
@@ -320,6 +332,24 @@ __global__ void __launch_bounds__(256) dequant_int4_kernel(const uint8_t* packed
 #pragma unroll
   for (int i = 0; i < 4; ++i) o.v[i] = __hfma(__float2half((float)q[i]), s, z);  // as-built reference: HFMA2, one rounding
   *reinterpret_cast<Vec4<__half>*>(out + r * 128 + lane * 4) = o;
+}
+
+__global__ void state_advance_kernel(long long* st, int n, int sink, int recent) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long total = st[1] + n;
+    st[0] += n;
+    st[1] = total;
+    long long lo = st[2];
+    if (total - recent > lo) lo = total - recent;
+    if (lo < sink) lo = sink;
+    st[2] = lo;
+  }
+}
+
+int launch_state_advance(long long* st, int n, int sink, int recent, cudaStream_t stream) {
+  state_advance_kernel<<<1, 32, 0, stream>>>(st, n, sink, recent);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
 }
 
 int launch_quant_int4(const void* in, long long in_row_stride, long long rows, void* packed, void* scale, void* zero,

@@ -108,6 +108,7 @@ class DuoKVCache:
         for l in range(num_layers):
             self.tensors.append(self._alloc_layer(l, self.full_cap_list[l], self.stage_cap_list[l]))
             self._make_handle(l)
+        self.dev_state = None        # optional device copy of (full_len, total, lo): see enable_device_state()
         self.launch_count = 0        # kernels of this library enqueued through this cache
         self.profile_events = None   # set to [] to collect (start, end) CUDA events around every duo_attention
         ws = self.lib.duo_workspace_bytes(self.batch_size, num_kv_heads, self.num_kv_groups, _C.DECODE_MAX_Q)
@@ -219,7 +220,51 @@ class DuoKVCache:
         return sc
 
     def state(self, l) -> _C.CacheState:
-        return _C.CacheState(self.kv_seq_len_list[l], self.total_list[l], self.lo_list[l])
+        ds = self.dev_state.data_ptr() if self.dev_state is not None else None
+        return _C.CacheState(self.kv_seq_len_list[l], self.total_list[l], self.lo_list[l], ds)
+
+    # ---- device-resident occupancy (CUDA-graph replay of decode steps) ---------------------------------
+    def enable_device_state(self):
+        """Keep a device copy of (full_len, total, lo) that the decode kernels read at launch, so that a captured
+        decode step can be replayed while the context grows.  All layers hold the same occupancy at step
+        boundaries, so one copy serves the whole cache."""
+        if self.dev_state is None:
+            self.dev_state = torch.zeros(4, dtype=torch.int64, device=self.device)
+            self._host_state = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.sync_device_state()
+        return self
+
+    def sync_device_state(self):
+        if self.dev_state is None:
+            return
+        l = self.num_layers - 1
+        self._host_state[0] = self.kv_seq_len_list[l]
+        self._host_state[1] = self.total_list[l]
+        self._host_state[2] = self.lo_list[l]
+        self.dev_state.copy_(self._host_state, non_blocking=True)
+
+    def advance_device(self, n):
+        """Enqueue full_len += n, total += n, lo = max(lo, total - recent, sink) on the device copy."""
+        _C.check(self.lib.duo_state_advance(self.dev_state.data_ptr(), int(n), self.sink_size, self.recent_size,
+                                            torch.cuda.current_stream(self.device).cuda_stream))
+        self.launch_count += 1
+
+    def snapshot_ring(self):
+        """Copy of the sink+ring slots of every layer (a few hundred KB each): lets a caller run throw-away steps
+        (CUDA-graph warm-up / capture) and put the streaming cache back exactly as it was."""
+        W = self.W
+        return [{k: v[:, :, :W].clone() for k, v in t.items() if k.startswith("ring")} for t in self.tensors]
+
+    def restore_ring(self, snap):
+        W = self.W
+        for t, sn in zip(self.tensors, snap):
+            for k, v in sn.items():
+                t[k][:, :, :W].copy_(v)
+
+    def advance_host(self, n):
+        """Mirror of advance_device for the host integers (call once per graph replay)."""
+        for l in range(self.num_layers):
+            self.advance(l, n)
 
     def advance(self, l, q_len):
         self.kv_seq_len_list[l] += q_len
@@ -243,12 +288,14 @@ class DuoKVCache:
             self.kv_seq_len_list[l] = 0
             self.total_list[l] = 0
             self.lo_list[l] = self.sink_size
+        self.sync_device_state()
 
     def evict_last(self, num_tokens):
         for l in range(self.num_layers):
             self.kv_seq_len_list[l] = max(0, self.kv_seq_len_list[l] - num_tokens)
             self.total_list[l], self.lo_list[l] = ring_evict(self.total_list[l], self.lo_list[l], num_tokens,
                                                              self.sink_size)
+        self.sync_device_state()
 
     @property
     def memory_usage(self):

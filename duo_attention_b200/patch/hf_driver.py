@@ -176,6 +176,8 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
                 x = all_reduce_sum(x, self._duo_tp_group)
             h = res + x
         h = base.norm(h[:, -1:, :])
+    if cache.dev_state is not None:  # device-resident occupancy (graph replay): advance it on the stream
+        cache.advance_device(S)
     logits = self.lm_head(h)
     if getattr(self, "_duo_logits_float", True):
         logits = logits.float()

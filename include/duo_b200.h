@@ -123,6 +123,12 @@ typedef struct duo_cache_state {
   int64_t full_len;
   int64_t total;
   int64_t lo;
+  /* Optional (may be NULL): device array {full_len, total, lo}.  When set, duo_rope_append, duo_attention (chunks
+   * of at most DUO_DECODE_MAX_Q tokens) and duo_stream_commit read the occupancy from DEVICE memory at kernel
+   * start, so a captured CUDA graph of a decode step can be replayed while the context grows; the host values
+   * above must then be upper-bound-consistent (they size the launch and drive the capacity checks).
+   * duo_state_advance moves the device copy forward after a step. */
+  const int64_t* device_state;
 } duo_cache_state;
 
 typedef struct duo_layer duo_layer; /* opaque: desc + pre-encoded TMA descriptors (host memory) */
@@ -169,6 +175,9 @@ DUO_API int duo_attention(const duo_layer* layer, const duo_cache_state* st, con
 DUO_API int duo_attention_mma(const duo_layer* layer, const duo_cache_state* st, const void* q, int64_t q_row_stride,
                               void* out, int32_t q_len, float scale, void* workspace, size_t workspace_bytes,
                               void* stream);
+
+/* device_state += n tokens: full_len += n, total += n, lo = max(lo, total - recent, sink) (one tiny kernel). */
+DUO_API int duo_state_advance(int64_t* device_state, int32_t n, int32_t sink, int32_t recent, void* stream);
 
 /* Move the tail of the staged chunk into sink/ring slots (call after duo_attention). */
 DUO_API int duo_stream_commit(const duo_layer* layer, const duo_cache_state* st, int32_t q_len, void* stream);

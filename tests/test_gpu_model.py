@@ -111,3 +111,33 @@ def test_static_cache_protocol_like_benchmark_static():
         assert cache.kv_seq_len == 0
         with pytest.raises(ValueError, match="max size 200"):
             model(input_ids=torch.zeros(1, 201, dtype=torch.long).cuda(), past_key_values=cache, use_cache=True)
+
+
+def test_cuda_graph_decode_matches_eager_decode():
+    """DuoDecodeGraph (one captured step, device-resident cache occupancy) == the eager driver, token by token,
+    across ring wrap-around and an evict_last in the middle."""
+    from duo_attention_b200.graph import DuoDecodeGraph
+
+    model = tiny_model("llama", seed=7)
+    gates = np.array([[1.0, 0.0], [0.0, 1.0]])
+    sink, recent = 4, 6
+    enable_llama_duo_attention_static_kv_cache_eval(model, gates)
+    model.cuda()
+    ca = DuoAttentionStaticKVCache(model, gates, 1, 256, sink, recent)
+    cb = DuoAttentionStaticKVCache(model, gates, 1, 256, sink, recent)
+    g = torch.Generator().manual_seed(4)
+    ids = torch.randint(0, 512, (1, 37), generator=g).cuda()
+    with torch.no_grad():
+        model(input_ids=ids, past_key_values=ca, use_cache=True)
+        model(input_ids=ids, past_key_values=cb, use_cache=True)
+        graph = DuoDecodeGraph(model, cb)
+        toks = torch.randint(0, 512, (20, 1, 1), generator=g).cuda()
+        for i in range(20):
+            want = model(input_ids=toks[i], past_key_values=ca, use_cache=True).logits
+            got = graph.step(toks[i])
+            torch.testing.assert_close(got.float(), want.float(), rtol=0, atol=0, msg=lambda m: f"step {i}: {m}")
+            assert ca.kv_seq_len == cb.kv_seq_len
+            if i == 9:
+                ca.evict_last(1)
+                cb.evict_last(1)
+                graph.resync()
