@@ -483,9 +483,15 @@ def main():
                                           "KV head + 1 layer of linears, extrapolated to 128+128 heads x 32 layers",
                                 "t_full_head_s": cb["t_full_head_s"]}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators captured inside the CUDA graph make destroy_process_group() hang: synchronise,
+        # release the graph and leave without the collective teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        graph = None
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def fa2_same_box(dev, ctx, chunk, prefill_ctx):
