@@ -221,3 +221,29 @@ def test_full_size_decode_properties(N):
         torch.testing.assert_close(o, t["full_v"][0, kvh, pos].float(), rtol=1e-2, atol=2e-3)
         t["full_k"][0, kvh, pos] = saved
         qkv.copy_(qkv_backup)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 prefill kernel (chunks >= 128 tokens) — shapes beyond the plain bf16 / B=1 / GQA-4 case, each
+# cross-checked against the oracle AND against the mma.sync kernel family on the same inputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [
+    dict(Hq=8, Hkv=2, n_full=1, sink=16, recent=48, chunks=[200, 128, 1, 333], B=2),             # batch 2
+    dict(Hq=8, Hkv=2, n_full=1, sink=16, recent=48, chunks=[256, 1, 130], dtype=torch.float16),  # fp16
+    dict(Hq=3, Hkv=3, n_full=1, sink=8, recent=24, chunks=[384, 129, 1, 257]),                   # MHA: token-tile pairs, odd tile counts
+    dict(Hq=8, Hkv=2, n_full=0, sink=64, recent=256, chunks=[500, 400, 1, 128]),                 # streaming heads only
+    dict(Hq=8, Hkv=2, n_full=2, sink=64, recent=256, chunks=[129, 1, 640]),                      # retrieval heads only
+    dict(Hq=12, Hkv=2, n_full=1, sink=4, recent=4, chunks=[128, 128, 128, 1, 128]),              # G=6, tiny window
+])
+def test_tc_prefill_shapes(kw):
+    kw = dict(kw)
+    run_schedule(seed=77, stage_cap=max(kw["chunks"]), **kw)
+    _, a = run_schedule(seed=78, stage_cap=max(kw["chunks"]), check=False, **kw)
+    _, b = run_schedule(seed=78, stage_cap=max(kw["chunks"]), check=False, force_mma=True, **kw)
+    for x, y in zip(a, b):
+        assert_parity(x, y, "tcgen05 vs mma.sync kernel family")
+
+
+def test_tc_prefill_sharp_softmax_rescales():
+    # growing logits force many reference updates (lazy rescale + mis-speculated tiles) in the tcgen05 kernel
+    run_schedule(8, 2, 1, 8, 24, [900, 300], seed=14, qscale=8.0, stage_cap=900)
