@@ -34,6 +34,16 @@ def pattern_dir(name):
 L3_8B = dict(hidden_size=4096, num_attention_heads=32, num_key_value_heads=8, head_dim=128, num_hidden_layers=32,
              intermediate_size=14336, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=3580165449.0,
              max_position_embeddings=1048576)
+ARCHS = {
+    # name: (model-config overrides, default attention pattern)  — dimensions from the public HF configs
+    "llama3-8b-1048k": (dict(), "Llama-3-8B-Instruct-Gradient-1048k"),
+    "llama3-8b-4194k": (dict(rope_theta=45315059621.0, max_position_embeddings=4194304),
+                        "Llama-3-8B-Instruct-Gradient-4194k"),
+    "mistral-7b-v0.3": (dict(vocab_size=32768, rope_theta=1000000.0, max_position_embeddings=32768),
+                        "Mistral-7B-Instruct-v0.3"),
+    "llama2-7b-32k": (dict(num_key_value_heads=32, intermediate_size=11008, vocab_size=32000, rope_theta=10000.0,
+                           max_position_embeddings=32768), "Llama-2-7B-32K-Instruct"),
+}
 SINK, RECENT = 64, 256
 METRIC = "decode tok/s @1M ctx (+ prefill tok/s @128K in `prefill`), Llama-3-8B, DuoAttention 50% retrieval heads"
 
@@ -52,22 +62,28 @@ def parse():
     ap.add_argument("--kv-format", default="bf16", choices=["bf16", "int4"],
                     help="int4 = BASELINE configs[3]: fp16 activations, INT4 KV with fused dequant (linears stay 16-bit: "
                          "the reference's W8A8 linears are QServe's, absent here)")
-    ap.add_argument("--pattern", default="Llama-3-8B-Instruct-Gradient-1048k")
+    ap.add_argument("--arch", default="llama3-8b-1048k", choices=sorted(ARCHS),
+                    help="other BASELINE configs (parity-test architectures); the headline line is the default")
+    ap.add_argument("--pattern", default=None, help="attn_patterns/<name>; default: the architecture's own")
+    ap.add_argument("--sparsity", type=float, default=0.5)
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fa2", action="store_true", help="skip the same-box FlashAttention-2 micro-comparison")
     ap.add_argument("--no-graph", action="store_true", help="drive decode eagerly instead of replaying a CUDA graph")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.pattern is None:
+        args.pattern = ARCHS[args.arch][1]
+    return args
 
 
-def head_pattern(name="Llama-3-8B-Instruct-Gradient-1048k"):
+def head_pattern(name="Llama-3-8B-Instruct-Gradient-1048k", sparsity=0.5):
     import numpy as np
 
     from duo_attn.utils import load_attn_pattern, sparsify_attention_heads
 
     gates, _, _ = load_attn_pattern(pattern_dir(name))
     np.random.seed(42)
-    mask, sp = sparsify_attention_heads(gates, None, 0.5)
+    mask, sp = sparsify_attention_heads(gates, None, sparsity)
     return mask, float(sp)
 
 
@@ -79,7 +95,7 @@ def decode_bytes_per_token(mask, ctx, row_bytes=256):
     return float(((n_f * (ctx + 1) + n_s * (SINK + RECENT + 1)) * 2 * row_bytes).sum())
 
 
-def prefill_flops(mask, n_ctx, chunk, G=4, D=128):
+def prefill_flops(mask, n_ctx, chunk, G=4, D=128):  # G = q heads per kv head of the architecture
     """Algorithmic attention FLOPs (4*D per visible (q,k) pair per q-head; masked halves not credited)."""
     W = SINK + RECENT
     full_pairs = n_ctx * (n_ctx + 1) // 2
@@ -140,7 +156,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mask, sp = head_pattern(args.pattern)
+    mask, sp = head_pattern(args.pattern, args.sparsity)
     vals = []
     for _ in range(max(1, min(args.steps, 3))):
         vals.append(cpu_reference_sample(args.ctx, mask))
@@ -161,7 +177,7 @@ def run_reference(args):
 
 def workload_config(args, sparsity):
     return {
-        "workload": f"Llama-3-8B-Instruct-Gradient-1048k arch (random init, bf16), DuoAttention pattern sparsity "
+        "workload": f"{args.arch} arch (random init, 16-bit), DuoAttention pattern {args.pattern} sparsity "
                     f"{sparsity:.2f}, sink {SINK}/recent {RECENT}, batch 1: decode @ctx={args.ctx} "
                     f"(evict_last(1) per step) + prefill {args.prefill_ctx} tokens in chunks of {args.chunk}",
         "pattern": args.pattern, "kv_format": args.kv_format, "ctx": args.ctx, "prefill_ctx": args.prefill_ctx, "chunk": args.chunk, "layers": args.layers,
@@ -231,12 +247,13 @@ def build_model(args, mask, rank, world, dev):
     from duo_attn.patch import enable_duo_attention_eval
 
     cfgd = dict(L3_8B)
+    cfgd.update(ARCHS[args.arch][0])
     cfgd["num_hidden_layers"] = args.layers
     plan = tp.plan_heads(mask[: args.layers], world)  # which (reordered) kv heads each rank owns, per layer
     local_mask = plan.local_mask(rank)
-    cfgd["num_attention_heads"] = L3_8B["num_attention_heads"] // world
-    cfgd["num_key_value_heads"] = L3_8B["num_key_value_heads"] // world
-    cfgd["intermediate_size"] = L3_8B["intermediate_size"] // world
+    cfgd["num_attention_heads"] = cfgd["num_attention_heads"] // world
+    cfgd["num_key_value_heads"] = cfgd["num_key_value_heads"] // world
+    cfgd["intermediate_size"] = cfgd["intermediate_size"] // world
     cfg = LlamaConfig(**cfgd, attn_implementation="eager")
     with torch.device("meta"):
         model = LlamaForCausalLM(cfg)
@@ -297,10 +314,10 @@ def main():
     from duo_attn.patch import DuoAttentionStaticKVCache
 
     _C.load()  # fail loudly if the CUDA extension is missing
-    mask, sparsity = head_pattern(args.pattern)
+    mask, sparsity = head_pattern(args.pattern, args.sparsity)
     mask = mask[: args.layers]
     model, local_mask = build_model(args, mask, rank, world, dev)
-    vocab = L3_8B["vocab_size"]
+    vocab = {**L3_8B, **ARCHS[args.arch][0]}["vocab_size"]
 
     def barrier():
         if world > 1:
@@ -353,7 +370,7 @@ def main():
             cache.profile_events = None
             launches_prefill = cache.launch_count + ops.LAUNCHES - c0
         ms = min(times)
-        fl = prefill_flops(mask, args.prefill_ctx, args.chunk)
+        fl = prefill_flops(mask, args.prefill_ctx, args.chunk, G=32 // mask.shape[1])
         peaks = load_peaks()
         attn_ms = max_over_ranks(attn_ms)
         result["prefill"] = {
@@ -469,7 +486,7 @@ def main():
         "a100_published": {"decode_ms_per_tok_1M": 55.0, "note": "reference figure, 1xA100-80G, other hardware"},
     }
     line.update(result)
-    if world == 1 and args.kv_format == "bf16" and not args.no_fa2:
+    if world == 1 and args.kv_format == "bf16" and not args.no_fa2 and args.arch == "llama3-8b-1048k":
         del cache
         torch.cuda.empty_cache()
         try:
