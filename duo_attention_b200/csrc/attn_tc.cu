@@ -292,15 +292,17 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         const bool more = j + 1 < n_tiles;
+        // Operand tiles first: these barriers completed long ago (their loads were released one or two tiles back),
+        // but even a successful mbarrier test costs ~100 cycles on the issuing thread (clock64 measurement) — pay
+        // that while the softmax warps are still producing P, not between MMAs where the tensor pipe would idle.
+        if (more) mbar_wait(&bars.k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        mbar_wait(&bars.v_full[st], ph);
         // ---- tile 0: PV0(j) then S0(j+1)
         mbar_wait(&bars.p_full[0], j & 1);
-        mbar_wait(&bars.v_full[st], ph);
         tc_fence_after();
         issue_pv(0, j);
         umma_commit(&bars.o_done[0]);
         if (more) {
-          mbar_wait(&bars.k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
           issue_s(0, j + 1);
           umma_commit(&bars.s_full[0]);
         }

@@ -4,7 +4,7 @@
 #   launches_prefill.csv   every kernel launch of ONE timed 128K prefill (nvtx range timed_prefill)
 #   prof_decode.ncu-rep    `--set full` capture of the split-KV decode kernel (2 launches of a decode step)
 #   prof_prefill.ncu-rep   `--set full` capture of the tcgen05 prefill kernel on one layer's last 32K chunk
-#                          (scratch/bench_tc.py: 32K queries over 96K past, n_full = 4)
+#                          (profiles/bench_tc.py: 32K queries over 96K past, n_full = 4)
 # Numbers printed by a run under ncu are never bench values.
 set -x
 mkdir -p gpurun_out
@@ -17,5 +17,5 @@ $NCU --set full --import-source on -k regex:duo_attn_mma_kernel -s 200 -c 2 -o g
 $NCU --nvtx --nvtx-include "timed_prefill/" --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_prefill.csv \
     python bench.py $COMMON --prefill-reps 1 > gpurun_out/ncu_prefill_stdout.log 2>&1
 $NCU --set full --import-source on -k regex:duo_attn_tc_kernel -s 2 -c 1 -o gpurun_out/prof_prefill \
-    python scratch/bench_tc.py > gpurun_out/ncu_prefill_full_stdout.log 2>&1
+    python profiles/bench_tc.py > gpurun_out/ncu_prefill_full_stdout.log 2>&1
 ls -la gpurun_out/
