@@ -71,6 +71,7 @@ def import_reference():
     for k in [k for k in sys.modules if k == "duo_attn" or k.startswith("duo_attn.")]:
         del sys.modules[k]
     import duo_attn.patch.llama as ref_llama
+    import duo_attn.patch.mistral as ref_mistral
     import duo_attn.patch.utils as ref_putils
 
     try:
@@ -78,14 +79,14 @@ def import_reference():
     except Exception as e:  # pragma: no cover - only if more stubs are needed
         print("duo_attn.utils import failed:", repr(e))
         ref_utils = None
-    return ref_llama, ref_putils, ref_utils
+    return ref_llama, ref_mistral, ref_putils, ref_utils
 
 
 def main():
     from oracle import duo_oracle as O
     import golden_cases as GC
 
-    ref_llama, ref_putils, ref_utils = import_reference()
+    ref_llama, ref_mistral, ref_putils, ref_utils = import_reference()
     assert ref_llama.__file__.startswith(REF), ref_llama.__file__
 
     # swap the CUDA-only third-party calls for the contract restatements
@@ -98,6 +99,8 @@ def main():
         return q, k
 
     ref_llama.apply_rope_inplace = rope_inplace
+    ref_mistral.flash_attn_func = O.flash_attn_contract
+    ref_mistral.apply_rope_inplace = rope_inplace
 
     # ---------------------------------------------------------------- attention-layer fixtures
     for case in GC.LAYER_CASES:
@@ -140,6 +143,39 @@ def main():
             **{k: np.int64(v) for k, v in extra.items()},
         )
         print("wrote layer", name, "tokens", sum(c.shape[1] for c in data["chunks"]), extra)
+        # the Mistral twin (duo_attn/patch/mistral.py:146-434): same cases through the reference's mistral
+        # forwards; SURVEY §2.1 found the two files identical modulo names — pinned here by running both.
+        if name in GC.MISTRAL_CASES:
+            mod = GC.RefAttnModule(case, data, ref_putils)
+            outs_m = []
+            if case["path"] == "tuple":
+                past, pos = None, 0
+                for hs in data["chunks"]:
+                    S = hs.shape[1]
+                    out, _, past = ref_mistral.mistral_duo_attention_forward_one_way_reordered(
+                        mod, hs, position_ids=torch.arange(pos, pos + S)[None], past_key_value=past, use_cache=True)
+                    outs_m.append(out)
+                    pos += S
+            else:
+                cache = ref_mistral.DuoAttentionStaticKVCache(
+                    GC.FakeModel(case, mod), [data["gate"].numpy()], data["B"], case["max_size"], case["sink"],
+                    case["recent"])
+                pos = 0
+                for i, hs in enumerate(data["chunks"]):
+                    S = hs.shape[1]
+                    out, _ = ref_mistral.mistral_duo_attention_forward_one_way_reordered_static(
+                        mod, hs, position_ids=torch.arange(pos, pos + S)[None], kv_cache=cache, layer_idx=0)
+                    outs_m.append(out)
+                    pos += S
+                    ev = case.get("evict_after", {}).get(i, 0)
+                    if ev:
+                        cache.evict_last(ev)
+                        pos -= ev
+            same = torch.equal(torch.cat(outs_m, dim=1), torch.cat(outs, dim=1))
+            np.savez_compressed(os.path.join(HERE, f"layer_mistral_{name}.npz"),
+                                out=torch.cat(outs_m, dim=1).numpy().astype(np.float32),
+                                identical_to_llama=np.bool_(same), checksum=np.float64(GC.checksum(data)))
+            print("wrote mistral twin", name, "identical to llama:", same)
 
     # ---------------------------------------------------------------- reorder fixtures
     for case in GC.REORDER_CASES:

@@ -27,6 +27,8 @@ LAYER_CASES = [
          chunks=[10, 10, 1, 1, 30, 1], B=1, seed=22, theta=10000.0, rope_factor=8.0, max_size=64),
 ]
 
+MISTRAL_CASES = ("tuple_g4_deploy", "static_g4_evict")  # also run through the reference's mistral.py twin
+
 REORDER_CASES = [
     dict(name="q_out_bias", seed=1, **{"in": 24, "out": 48}, bias=True, gate=[0.9, 0.1, 0.7, 0.2], repeat=12,
          channel="out"),

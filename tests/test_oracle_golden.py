@@ -98,3 +98,17 @@ def test_flash_contract_bottom_right_and_gqa():
                 s = (q[b, i, h] @ k[b, :vis, h // 2].T) / 8 ** 0.5
                 ref = torch.softmax(s, -1) @ v[b, :vis, h // 2]
                 torch.testing.assert_close(out[b, i, h], ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", GC.MISTRAL_CASES)
+def test_oracle_matches_reference_mistral_twin(name):
+    """The same oracle serves Mistral: the reference's mistral.py forwards produce bit-identical outputs to its
+    llama.py forwards on these cases (recorded when the fixtures were generated), and the oracle matches both."""
+    case = next(c for c in GC.LAYER_CASES if c["name"] == name)
+    gold = np.load(os.path.join(GOLD, f"layer_mistral_{name}.npz"))
+    assert bool(gold["identical_to_llama"])
+    data = GC.make_layer_inputs(case)
+    assert abs(GC.checksum(data) - float(gold["checksum"])) < 1e-6 * abs(float(gold["checksum"]))
+    with torch.no_grad():
+        out, _ = run_oracle_layer(case, data)
+    np.testing.assert_allclose(out.numpy(), gold["out"], rtol=1e-5, atol=1e-6)
