@@ -425,7 +425,7 @@ def main():
         attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events) / args.steps
         n_attn = len(cache.profile_events) // args.steps
         cache.profile_events = None
-        if not args.no_graph:
+        if not args.no_graph and args.kv_format == "bf16":  # INT4 caches are driven eagerly (graph.py)
             from duo_attention_b200.graph import DuoDecodeGraph
 
             graph = DuoDecodeGraph(model, cache)
@@ -474,7 +474,7 @@ def main():
         "config": workload_config(args, sparsity),
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": 8,
                 "d2h_bytes_per_step": 8},
-        "gpu_launches": launches, "decode_driver": "eager" if args.no_graph else "cuda-graph replay (DuoDecodeGraph)",
+        "gpu_launches": launches, "decode_driver": "cuda-graph replay (DuoDecodeGraph)" if graph is not None else "eager",
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None,

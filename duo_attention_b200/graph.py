@@ -17,6 +17,12 @@ import torch
 
 class DuoDecodeGraph:
     def __init__(self, model, cache, warmup: int = 2):
+        if cache.growable:
+            raise ValueError("DuoDecodeGraph needs a pre-allocated cache (DuoAttentionStaticKVCache): a growable "
+                             "cache may be re-allocated, which would leave stale pointers in the captured graph")
+        if cache.kv_format != "same":
+            raise ValueError("DuoDecodeGraph: INT4 caches are driven eagerly for now (the device-state path of the "
+                             "INT4 kernel has not been validated on hardware yet)")
         self.model, self.cache = model, cache
         dev = cache.device
         B = cache.batch_size

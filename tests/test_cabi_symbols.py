@@ -61,5 +61,7 @@ def test_sass_has_tma_and_tensor_core_instructions():
     except FileNotFoundError:
         pytest.skip("cuobjdump not available")
     assert "sm_100a" in sass or "SM100a" in sass or "EF_CUDA_SM100" in sass
-    assert "UTMALDG" in sass
-    assert "HMMA" in sass or "UTCHMMA" in sass
+    # the SASS names of the PTX the kernels are written in (B200_PROFILING.md): TMA tiled loads, tcgen05.mma,
+    # tcgen05.ld / tcgen05.st, cp.async (INT4 tiles) and the mma.sync used by the HBM-bound decode kernel
+    for mnemonic in ("UTMALDG", "UTCHMMA", "LDTM", "STTM", "LDGSTS", "HMMA", "SYNCS", "UTCBAR"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS of libduo_b200.so"
