@@ -45,6 +45,10 @@ ARCHS = {
                            max_position_embeddings=32768), "Llama-2-7B-32K-Instruct"),
 }
 SINK, RECENT = 64, 256
+# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the decode kernel, divided by the
+# algorithmic bytes of that launch (profiles/r1_decode.md: 3.2224 GB + 0.0040 GB measured for the n_full = 6 layer
+# at 1,048,576 tokens whose algorithmic traffic is 3.2212 GB; 2.1489 GB vs 2.1475 GB for an n_full = 4 layer)
+NCU_DECODE_TRAFFIC_RATIO = 1.0016
 METRIC = "decode tok/s @1M ctx (+ prefill tok/s @128K in `prefill`), Llama-3-8B, DuoAttention 50% retrieval heads"
 
 
@@ -477,7 +481,12 @@ def main():
         "gpu_launches": launches, "decode_driver": "cuda-graph replay (DuoDecodeGraph)" if graph is not None else "eager",
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": (by / max(n_attn, 1) * NCU_DECODE_TRAFFIC_RATIO) if args.kv_format == "bf16" else None,
+                     "traffic_note": "bytes per average launch = algorithmic bytes per launch x the DRAM/algorithmic "
+                                     "ratio of the ncu --set full capture (profiles/r1_decode.md)",
+                     "achieved_note": "algorithmic bytes of the 32 attention launches of a step / sum of their "
+                                      "CUDA-event durations (eager pass on the launching stream)",
                      "kernel": ("duo_attn_int4_kernel" if args.kv_format == "int4" else "duo_attn_mma_kernel")
                                + " (decode, all layers of one step)",
                      "attn_ms_per_step": attn_ms, "attn_ms_per_step_max_rank": attn_ms_max,
