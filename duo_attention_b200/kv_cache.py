@@ -380,3 +380,15 @@ class DuoAttentionStaticKVCache(DuoKVCache):
             kv_format=kv_format,
             growable=False,
         )
+
+
+class DuoAttentionStaticINT4KVCache(DuoAttentionStaticKVCache):
+    """Drop-in for the demo's INT4 cache (demo/int4_kv.py:115-260): same constructor arguments.  Storage is the
+    packed-nibble + fp16 scale/zero format of demo/quantize_int4.cu in head-major order; there is no fp16 scratch
+    copy of the cache and no per-step ``get()`` dequantisation pass — the attention kernel dequantises in its
+    K/V load stage.  The model must run in fp16, as in the demo (run_duo_w8a8kv4.py:41-45)."""
+
+    def __init__(self, model, full_attention_heads, batch_size, max_size, sink_size, recent_size,
+                 prefilling_chunk_size):
+        super().__init__(model, full_attention_heads, batch_size, max_size, sink_size, recent_size,
+                         prefilling_chunk_size=prefilling_chunk_size, kv_format="int4")

@@ -3,7 +3,7 @@ mistral.py:504-598): same function names, argument order and error behaviour; un
 forward calls the B200 kernels instead of FlashAttention-2 + torch.cat + cache copies."""
 from __future__ import annotations
 
-from ..kv_cache import DuoAttentionStaticKVCache, DuoKVCache
+from ..kv_cache import DuoAttentionStaticINT4KVCache, DuoAttentionStaticKVCache, DuoKVCache
 from .hf_driver import install as _install
 from .reorder import reorder_full_attn_heads, reorder_linear_weights
 
@@ -51,6 +51,7 @@ __all__ = [
     "enable_llama_duo_attention_static_kv_cache_eval",
     "enable_mistral_duo_attention_static_kv_cache_eval",
     "DuoAttentionStaticKVCache",
+    "DuoAttentionStaticINT4KVCache",
     "DuoKVCache",
     "reorder_linear_weights",
     "reorder_full_attn_heads",
