@@ -20,6 +20,8 @@
 // Tiles (64 keys: 4 KB K + 4 KB V + 4 x 128 B scale/zero = 8.5 KB instead of 32 KB) are fetched with 16 B
 // cp.async (zero-fill beyond the valid rows) into a 4-stage ring.  Same work decomposition, masks, split-KV merge
 // and variants as attn_mma.cu.  Activations are fp16 (the reference's INT4 demo runs in fp16).
+#include <cstdlib>
+
 #include "duo_common.cuh"
 
 namespace duo {
@@ -559,6 +561,520 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
   if (tid == 0) p.counters[item] = 0;
 }
 
+// =============================================================================================
+// Decode variant with the operand roles swapped ("keys are M"): S^T = codes(K) . Q^T and O^T = codes(V)^T . P'^T.
+//
+// With group * q_len <= 8 query rows, the row-major formulation above pads them to the 16-row M dimension of
+// m16n8k16 (4 useful rows of 16 for a GQA-4 decode step).  Here the 16 KEYS of an m-tile are M and the query rows
+// are the 8-wide N dimension, which halves the HMMA count (34 instead of 64 per warp per 32 keys), the logits /
+// exponentials per thread (8 instead of 16) and the accumulator registers (32 instead of 64), so four CTAs fit on
+// an SM instead of two.  The nibble -> fp16 conversion is unchanged (the same LOP3 results now fill A fragments:
+// the A row-major and B col-major fragments of m16n8k16 map threads identically).  S^T leaves the QK^T product
+// in (key g | rows 2t,2t+1) order; P'^T must enter the PV product as (keys 2t,2t+1 | row g): one
+// movmatrix.trans per 8 keys.  sum_j fp16(p'_j) (the +1024 offset removal) is one extra HMMA against a
+// constant-one A fragment per 16 keys instead of unpack+add on the ALU pipe, and the running-max reduction
+// across lanes is only executed on tiles where some lane saw a logit above the running max.
+//
+// EXPERIMENTAL: selected only when the environment variable DUO_INT4_SWAPAB=1 is set (see launch_attn_int4).
+// The fragment algebra is checked lane-by-lane on the CPU in tests/test_int4_swapab_layout.py.
+// =============================================================================================
+constexpr int D8_TILE = 128;
+constexpr int D8_STAGES = 3;
+constexpr int D8_PACK = D8_TILE * 64;
+constexpr int D8_STAGE_BYTES = 2 * D8_PACK + 4 * D8_TILE * 2;
+constexpr int D8_ROWS = 8;
+constexpr int D8_SMEM_BYTES = D8_STAGES * D8_STAGE_BYTES + 128;
+static_assert(D8_STAGES * D8_STAGE_BYTES >= (4 * D8_ROWS * 128 + D8_ROWS * 128 + 5 * D8_ROWS * 2) * 4, "merge smem");
+
+// (w & mask) | 0x64006400 as ONE LOP3 (the C expression compiles to two, both with immediate operands)
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t w, uint32_t mask, uint32_t magic) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "r"(mask), "r"(magic));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop1_lo(uint32_t w) { return lop3_and_or(w, 0x000f000fu, 0x64006400u); }
+__device__ __forceinline__ uint32_t lop1_hi(uint32_t w) { return lop3_and_or(w, 0x00f000f0u, 0x64006400u); }
+__device__ __forceinline__ float lds_half(uint32_t addr) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+  return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+__global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const I4Params pin) {
+  I4Params p = pin;
+  if (pin.dstate) {
+    p.full_len = pin.dstate[0];
+    p.total = pin.dstate[1];
+    p.lo = pin.dstate[2];
+    const long long nk = p.full_len + p.q_len;
+    long long kps = (nk + p.splits_full - 1) / p.splits_full;
+    kps = (kps + D8_TILE - 1) / D8_TILE * D8_TILE;
+    p.keys_per_split = (int)(kps < D8_TILE ? D8_TILE : kps);
+    p.cache_scan = (int)(p.total < p.W ? p.total : p.W);
+  }
+  constexpr int KPW = 32;  // keys per warp per tile
+  using Op = MmaOp<__half>;
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int b = blockIdx.y;
+
+  const int n_full_items = p.n_full * p.splits_full;
+  int kvh, split;
+  bool is_full;
+  if ((int)blockIdx.x < n_full_items) {
+    is_full = true;
+    split = blockIdx.x % p.splits_full;
+    kvh = blockIdx.x / p.splits_full;
+  } else {
+    is_full = false;
+    kvh = p.n_full + (blockIdx.x - n_full_items);
+    split = 0;
+  }
+  const int rows_total = p.group * p.q_len;  // <= 8
+  const int tok_max = (rows_total - 1) / p.group;
+  long long a0, a1, b0 = 0, b1 = 0, base, slots;
+  const uint8_t *gk, *gv;
+  const __half *gks, *gkz, *gvs, *gvz;
+  if (is_full) {
+    base = p.full_len;
+    const long long nkeys = p.full_len + tok_max + 1;
+    a0 = (long long)split * p.keys_per_split;
+    a1 = min(nkeys, a0 + (long long)p.keys_per_split);
+    if (a1 < a0) a1 = a0;
+    slots = p.full_cap;
+    const long long hrow = ((long long)b * p.n_full + kvh) * p.full_cap;
+    gk = p.full_k + hrow * 64;
+    gv = p.full_v + hrow * 64;
+    gks = p.fks + hrow;
+    gkz = p.fkz + hrow;
+    gvs = p.fvs + hrow;
+    gvz = p.fvz + hrow;
+  } else {
+    base = p.stage_off;
+    a0 = 0;
+    a1 = p.cache_scan;
+    b0 = p.stage_off;
+    b1 = (long long)p.stage_off + tok_max + 1;
+    slots = p.ring_slots;
+    const long long hrow = ((long long)b * p.n_stream + (kvh - p.n_full)) * p.ring_slots;
+    gk = p.ring_k + hrow * 64;
+    gv = p.ring_v + hrow * 64;
+    gks = p.rks + hrow;
+    gkz = p.rkz + hrow;
+    gvs = p.rvs + hrow;
+    gvz = p.rvz + hrow;
+  }
+  const int nA = (int)((a1 - a0 + D8_TILE - 1) / D8_TILE);
+  const int nB = (int)((b1 - b0 + D8_TILE - 1) / D8_TILE);
+  const int n_tiles = nA + nB;
+  auto tile_start = [&](int i) -> long long {
+    return i < nA ? a0 + (long long)i * D8_TILE : b0 + (long long)(i - nA) * D8_TILE;
+  };
+  auto tile_end = [&](int i) -> long long { return i < nA ? a1 : b1; };
+
+  // loader: same tile image as duo_attn_int4_kernel<4>.  Interior tiles (every row valid) take a path with one
+  // address per thread and immediate offsets; boundary tiles predicate and zero-fill per row.
+  const int ld_r0 = tid >> 2, ld_c = tid & 3;
+  const uint32_t ld_doff = ld_r0 * 64 + ((ld_c ^ ((ld_r0 >> 1) & 3)) << 4);
+  const int ld_arr = (tid & 63) >> 4, ld_qd = tid & 15;  // scale/zero arrays: 4 arrays x 16 chunks of 8 rows
+  const __half* ld_src = ld_arr == 0 ? gks : ld_arr == 1 ? gkz : ld_arr == 2 ? gvs : gvz;
+  const uint32_t ld_soff = 2 * D8_PACK + ld_arr * (D8_TILE * 2) + ld_qd * 16;
+  auto issue = [&](int i) {
+    if (i < n_tiles) {
+      const long long j0 = tile_start(i);
+      const long long lim = min(tile_end(i), slots);  // rows >= lim are not read (zero-filled)
+      const uint32_t sbase = smem_u32(smem + (i % D8_STAGES) * D8_STAGE_BYTES);
+      if (j0 + D8_TILE <= lim) {
+        const long long off = (j0 + ld_r0) * 64 + ld_c * 16;
+        const uint8_t* kp = gk + off;
+        const uint8_t* vp = gv + off;
+#pragma unroll
+        for (int it = 0; it < D8_TILE * 4 / I4_THREADS; ++it) {
+          cp_async16(sbase + ld_doff + it * 2048, kp + it * 2048, 16);
+          cp_async16(sbase + D8_PACK + ld_doff + it * 2048, vp + it * 2048, 16);
+        }
+        if (tid < D8_TILE / 2) cp_async16(sbase + ld_soff, ld_src + j0 + ld_qd * 8, 16);
+      } else {
+#pragma unroll
+        for (int it = 0; it < D8_TILE * 4 / I4_THREADS; ++it) {
+          const int r = ld_r0 + it * 32;
+          const bool ok = (j0 + r) < lim;
+          const long long srow = ok ? (j0 + r) : 0;
+          cp_async16(sbase + ld_doff + it * 2048, gk + srow * 64 + ld_c * 16, ok ? 16 : 0);
+          cp_async16(sbase + D8_PACK + ld_doff + it * 2048, gv + srow * 64 + ld_c * 16, ok ? 16 : 0);
+        }
+        if (tid < D8_TILE / 2) {
+          const long long r0 = j0 + ld_qd * 8;
+          long long nb = (lim - r0) * 2;
+          nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+          cp_async16(sbase + ld_soff, ld_src + (nb > 0 ? r0 : 0), (int)nb);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < D8_STAGES - 1; ++i) issue(i);
+
+  // ---- Q^T as B fragments: lane (g, t4) holds query row g, head_dim chunk 32 t4 .. 32 t4 + 31 ------------
+  const int wkey = warp * KPW;
+  uint32_t qb[8][2];
+  float qsum[2], qoff[2];
+  int tok_r[2];
+  {
+    const __half* qbase = reinterpret_cast<const __half*>(p.q) + (long long)b * p.q_batch_stride;
+    const bool ok = g < rows_total;
+    const int tok = ok ? g / p.group : 0;
+    const int hq = kvh * p.group + (ok ? g % p.group : 0);
+    const __half* src = qbase + (long long)tok * p.q_tok_stride + (long long)hq * kHeadDim + 32 * t4;
+    float s_all = 0.f, s_off = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      __half e[8];
+      if (ok) {
+        *reinterpret_cast<uint4*>(e) = *reinterpret_cast<const uint4*>(src + 8 * w);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = __float2half(0.f);
+      }
+      const __half sixteenth = __float2half(0.0625f);
+      const __half h0 = __hmul(e[0], sixteenth), h4 = __hmul(e[4], sixteenth);
+      const __half h2 = __hmul(e[2], sixteenth), h6 = __hmul(e[6], sixteenth);
+      qb[2 * w][0] = Op::pack(__half2float(e[1]), __half2float(e[5]));      // k = 2t,2t+1   <- d+1, d+5
+      qb[2 * w][1] = Op::pack(__half2float(h0), __half2float(h4));          // k = 2t+8,+9   <- (d+0, d+4)/16
+      qb[2 * w + 1][0] = Op::pack(__half2float(e[3]), __half2float(e[7]));  //               <- d+3, d+7
+      qb[2 * w + 1][1] = Op::pack(__half2float(h2), __half2float(h6));      //               <- (d+2, d+6)/16
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_all += __half2float(e[i]);
+      s_off += 1024.f * (__half2float(e[1]) + __half2float(e[5]) + __half2float(e[3]) + __half2float(e[7]) +
+                         __half2float(h0) + __half2float(h4) + __half2float(h2) + __half2float(h6));
+    }
+    s_all += __shfl_xor_sync(0xffffffffu, s_all, 1);
+    s_all += __shfl_xor_sync(0xffffffffu, s_all, 2);
+    s_off += __shfl_xor_sync(0xffffffffu, s_off, 1);
+    s_off += __shfl_xor_sync(0xffffffffu, s_off, 2);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {  // accumulator columns of this lane are query rows 2 t4, 2 t4 + 1
+      const int r = 2 * t4 + e;
+      qsum[e] = __shfl_sync(0xffffffffu, s_all, r * 4);
+      qoff[e] = __shfl_sync(0xffffffffu, s_off, r * 4);
+      tok_r[e] = r < rows_total ? r / p.group : -1;
+    }
+  }
+
+  float oT[8][4];  // tile call*4 + i: rows of the tile are head_dim 32 (2 call) + 4 g + i  and  32 (2 call + 1) + 4 g + i
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oT[i][0] = oT[i][1] = oT[i][2] = oT[i][3] = 0.f;
+  float psT[4] = {0.f, 0.f, 0.f, 0.f};  // sum_j fp16(p'_j) per query row, from the constant-one HMMA
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};   // per-lane partial of sum p      (keys = g mod 8)
+  float pz_run[2] = {0.f, 0.f};  // per-lane partial of sum p z_v
+  const uint32_t ones[4] = {0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u};
+  const int lrow = lane & 7, lmat = lane >> 3;
+
+  for (int i = 0; i < n_tiles; ++i) {
+    cp_async_wait<D8_STAGES - 2>();
+    __syncthreads();
+    issue(i + D8_STAGES - 1);
+    const uint8_t* st = smem + (i % D8_STAGES) * D8_STAGE_BYTES;
+    const uint32_t sK = smem_u32(st), sV = sK + D8_PACK;
+    const uint32_t sKs = sK + 2 * D8_PACK, sKz = sKs + 2 * D8_TILE, sVs = sKs + 4 * D8_TILE, sVz = sKs + 6 * D8_TILE;
+    const long long j0 = tile_start(i);
+    const long long jend = tile_end(i);
+
+    // ---- S^T_raw = codes(K) . Q^T : 2 m-tiles of 16 keys ----------------------------------------------------
+    float sc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      sc[mt][0] = sc[mt][1] = sc[mt][2] = sc[mt][3] = 0.f;
+      const int key0 = wkey + mt * 16 + g, key1 = key0 + 8;
+      const uint32_t addr0 = sK + key0 * 64 + ((t4 ^ ((key0 >> 1) & 3)) << 4);
+      const uint32_t addr1 = sK + key1 * 64 + ((t4 ^ ((key1 >> 1) & 3)) << 4);
+      uint32_t x[4], y[4];
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(addr0));
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]) : "r"(addr1));
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t xl = x[w], yl = y[w], xh = xl >> 8, yh = yl >> 8;
+        const uint32_t fa[4] = {lop1_lo(xl), lop1_lo(yl), lop1_hi(xl), lop1_hi(yl)};
+        Op::run(sc[mt], fa, qb[2 * w][0], qb[2 * w][1]);
+        const uint32_t fb[4] = {lop1_lo(xh), lop1_lo(yh), lop1_hi(xh), lop1_hi(yh)};
+        Op::run(sc[mt], fb, qb[2 * w + 1][0], qb[2 * w + 1][1]);
+      }
+    }
+    // ---- logits s_j (S_raw - qoff) + z_j qsum; mask on boundary tiles -----------------------------------------
+    const long long kfirst = j0 + wkey;
+    const bool need_mask = (kfirst + KPW > jend) || (kfirst + KPW - 1 > base) || (!is_full && i < nA);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int hk = 0; hk < 2; ++hk) {
+        const int key = wkey + mt * 16 + hk * 8 + g;
+        const float ks = lds_half(sKs + 2 * key), kz = lds_half(sKz + 2 * key);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) sc[mt][hk * 2 + e] = ks * (sc[mt][hk * 2 + e] - qoff[e]) + kz * qsum[e];
+      }
+    }
+    if (need_mask) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int hk = 0; hk < 2; ++hk) {
+          const long long j = kfirst + mt * 16 + hk * 8 + g;
+          bool kvis = j < jend;
+          if (!is_full && i < nA) kvis = kvis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int tk = tok_r[e];
+            if (!(kvis && tk >= 0 && j <= base + tk)) sc[mt][hk * 2 + e] = -INFINITY;
+          }
+        }
+      }
+    }
+    // ---- running max: cross-lane reduction only when some lane saw a logit above it ----------------------------
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      mx[0] = fmaxf(mx[0], fmaxf(sc[mt][0], sc[mt][2]));
+      mx[1] = fmaxf(mx[1], fmaxf(sc[mt][1], sc[mt][3]));
+    }
+    const bool moved = __any_sync(0xffffffffu, (mx[0] > m_run[0]) || (mx[1] > m_run[1]));
+    if (moved) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        mx[e] = fmaxf(mx[e], __shfl_xor_sync(0xffffffffu, mx[e], 4));
+        mx[e] = fmaxf(mx[e], __shfl_xor_sync(0xffffffffu, mx[e], 8));
+        mx[e] = fmaxf(mx[e], __shfl_xor_sync(0xffffffffu, mx[e], 16));
+      }
+      float alpha[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float m_new = fmaxf(m_run[e], mx[e]);
+        const float msn = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+        alpha[e] = (m_run[e] == -INFINITY) ? 0.f : fast_exp2(m_run[e] * p.scale_log2 - msn);
+        m_run[e] = m_new;
+        l_run[e] *= alpha[e];
+        pz_run[e] *= alpha[e];
+        psT[e] *= alpha[e];
+        psT[e + 2] *= alpha[e];
+      }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        oT[d][0] *= alpha[0];
+        oT[d][1] *= alpha[1];
+        oT[d][2] *= alpha[0];
+        oT[d][3] *= alpha[1];
+      }
+    }
+    float msc[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) msc[e] = (m_run[e] == -INFINITY) ? 0.f : m_run[e] * p.scale_log2;
+    // ---- p = 2^(s - m), p' = fp16(p s_v); transpose to the B-fragment order --------------------------------------
+    uint32_t pb[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int hk = 0; hk < 2; ++hk) {
+        const int key = wkey + mt * 16 + hk * 8 + g;
+        const float vs = lds_half(sVs + 2 * key), vz = lds_half(sVz + 2 * key);
+        const float p0 = fast_exp2(sc[mt][hk * 2 + 0] * p.scale_log2 - msc[0]);
+        const float p1 = fast_exp2(sc[mt][hk * 2 + 1] * p.scale_log2 - msc[1]);
+        l_run[0] += p0;
+        l_run[1] += p1;
+        pz_run[0] += p0 * vz;
+        pz_run[1] += p1 * vz;
+        const __half2 a = __floats2half2_rn(p0 * vs, p1 * vs);  // (key | rows 2t, 2t+1)
+        pb[mt][hk] = movm_trans(*reinterpret_cast<const uint32_t*>(&a));  // -> (keys 2t, 2t+1 | row g)
+      }
+    }
+    // ---- O^T_raw += codes(V)^T . P'^T ------------------------------------------------------------------------------
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+      Op::run(psT, ones, pb[k2][0], pb[k2][1]);
+#pragma unroll
+      for (int call = 0; call < 2; ++call) {
+        const int key = wkey + k2 * 16 + (lmat & 1) * 8 + lrow;
+        const int blk = 2 * call + (lmat >> 1);
+        const uint32_t addr = sV + key * 64 + ((blk ^ ((key >> 1) & 3)) << 4);
+        uint32_t r0, r1, r2, r3;  // (keys 0-7, blk 2c) (keys 8-15, blk 2c) (keys 0-7, blk 2c+1) (keys 8-15, blk 2c+1)
+        ldsm_x4_trans(r0, r1, r2, r3, addr);
+        const uint32_t h0 = r0 >> 8, h1 = r1 >> 8, h2 = r2 >> 8, h3 = r3 >> 8;
+        const uint32_t f1[4] = {lop1_lo(r0), lop1_lo(r2), lop1_lo(r1), lop1_lo(r3)};
+        Op::run(oT[call * 4 + 1], f1, pb[k2][0], pb[k2][1]);  // i = 1
+        const uint32_t f0[4] = {lop1_hi(r0), lop1_hi(r2), lop1_hi(r1), lop1_hi(r3)};
+        Op::run(oT[call * 4 + 0], f0, pb[k2][0], pb[k2][1]);  // i = 0 (x16)
+        const uint32_t f3[4] = {lop1_lo(h0), lop1_lo(h2), lop1_lo(h1), lop1_lo(h3)};
+        Op::run(oT[call * 4 + 3], f3, pb[k2][0], pb[k2][1]);  // i = 3
+        const uint32_t f2[4] = {lop1_hi(h0), lop1_hi(h2), lop1_hi(h1), lop1_hi(h3)};
+        Op::run(oT[call * 4 + 2], f2, pb[k2][0], pb[k2][1]);  // i = 2 (x16)
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+#pragma unroll
+    for (int sh = 4; sh <= 16; sh <<= 1) {
+      l_run[e] += __shfl_xor_sync(0xffffffffu, l_run[e], sh);
+      pz_run[e] += __shfl_xor_sync(0xffffffffu, pz_run[e], sh);
+    }
+  }
+
+  // ---- true (un-normalised) O of this warp -> shared memory in natural head_dim order, then merge the 4 warps ----
+  __syncthreads();
+  float* w_o = reinterpret_cast<float*>(smem);   // [4][8][128]
+  float* sm_o = w_o + 4 * D8_ROWS * 128;         // [8][128]
+  float* w_ml = sm_o + D8_ROWS * 128;            // [4][8][2]
+  float* sm_ml = w_ml + 4 * D8_ROWS * 2;         // [8][2]
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int r = 2 * t4 + e;
+    if (g == 0) {
+      w_ml[(warp * D8_ROWS + r) * 2 + 0] = (m_run[e] == -INFINITY) ? -INFINITY : m_run[e] * p.scale_log2;
+      w_ml[(warp * D8_ROWS + r) * 2 + 1] = l_run[e];
+    }
+    const float off = 1024.f * psT[e];
+#pragma unroll
+    for (int tl = 0; tl < 8; ++tl) {
+      const int call = tl >> 2, ii = tl & 3;
+      const float mul = (ii & 1) ? 1.f : 0.0625f;
+#pragma unroll
+      for (int hm = 0; hm < 2; ++hm) {
+        const int d = 32 * (2 * call + hm) + 4 * g + ii;
+        w_o[(warp * D8_ROWS + r) * 128 + d] = (oT[tl][hm * 2 + e] - off) * mul + pz_run[e];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < D8_ROWS * 128; idx += I4_THREADS) {
+    const int r = idx >> 7, d = idx & 127;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) mm = fmaxf(mm, w_ml[(w * D8_ROWS + r) * 2]);
+    float acc = 0.f, ll = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = w_ml[(w * D8_ROWS + r) * 2];
+      const float f = (mw == -INFINITY) ? 0.f : fast_exp2(mw - mm);
+      acc += f * w_o[(w * D8_ROWS + r) * 128 + d];
+      ll += f * w_ml[(w * D8_ROWS + r) * 2 + 1];
+    }
+    sm_o[r * 128 + d] = acc;
+    if (d == 0) {
+      sm_ml[r * 2] = mm;
+      sm_ml[r * 2 + 1] = ll;
+    }
+  }
+  __syncthreads();
+
+  __half* outb = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_batch_stride;
+  auto store_row_elem = [&](int r, int d, float v0, float v1) {
+    const int tok = r / p.group;
+    const int hq = kvh * p.group + r % p.group;
+    __half* dst = outb + ((long long)tok * p.n_q_heads + hq) * kHeadDim + d;
+    *reinterpret_cast<uint32_t*>(dst) = Op::pack(v0, v1);
+  };
+  const int nsplit = is_full ? p.splits_full : 1;
+  if (nsplit == 1) {
+    for (int idx = tid; idx < rows_total * 64; idx += I4_THREADS) {
+      const int r = idx >> 6, d = (idx & 63) * 2;
+      const float l = sm_ml[r * 2 + 1];
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      store_row_elem(r, d, sm_o[r * 128 + d] * inv, sm_o[r * 128 + d + 1] * inv);
+    }
+    return;
+  }
+  // ---- split-KV publish + last-CTA merge (protocol of attn_mma.cu, 8 rows per item) --------------------------
+  const long long item = (long long)b * p.n_full + kvh;
+  float* wo = p.ws_o + (item * p.splits_full + split) * (long long)(D8_ROWS * 128);
+  float* wml = p.ws_ml + (item * p.splits_full + split) * (long long)(D8_ROWS * 2);
+  for (int idx = tid; idx < rows_total * 32; idx += I4_THREADS) {
+    const int r = idx >> 5, d4 = (idx & 31) * 4;
+    *reinterpret_cast<float4*>(&wo[r * 128 + d4]) = *reinterpret_cast<const float4*>(&sm_o[r * 128 + d4]);
+  }
+  if (tid < rows_total * 2) wml[tid] = sm_ml[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(&p.counters[item], 1);
+    s_is_last = (prev == p.splits_full - 1);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const float* po = p.ws_o + item * p.splits_full * (long long)(D8_ROWS * 128);
+  const float* pml = p.ws_ml + item * p.splits_full * (long long)(D8_ROWS * 2);
+  float* cm_o = w_o;    // [4 warps][8 rows][128]
+  float* cm_ml = w_ml;  // [4 warps][8 rows][2]
+  for (int r = 0; r < rows_total; ++r) {
+    float mm = -INFINITY, ll = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = warp; s0 < p.splits_full; s0 += 16) {
+      float ms[4], ls[4];
+      float4 vs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s2 = s0 + 4 * u;
+        const bool ok = s2 < p.splits_full;
+        const int sc2 = ok ? s2 : s0;
+        ms[u] = ok ? __ldcg(&pml[(sc2 * D8_ROWS + r) * 2]) : -INFINITY;
+        ls[u] = __ldcg(&pml[(sc2 * D8_ROWS + r) * 2 + 1]);
+        vs[u] = __ldcg(reinterpret_cast<const float4*>(&po[((long long)sc2 * D8_ROWS + r) * 128 + lane * 4]));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ms[u] == -INFINITY) continue;
+        const float mn = fmaxf(mm, ms[u]);
+        const float fo = (mm == -INFINITY) ? 0.f : fast_exp2(mm - mn);
+        const float fn = fast_exp2(ms[u] - mn);
+        acc.x = acc.x * fo + vs[u].x * fn;
+        acc.y = acc.y * fo + vs[u].y * fn;
+        acc.z = acc.z * fo + vs[u].z * fn;
+        acc.w = acc.w * fo + vs[u].w * fn;
+        ll = ll * fo + ls[u] * fn;
+        mm = mn;
+      }
+    }
+    *reinterpret_cast<float4*>(&cm_o[(warp * D8_ROWS + r) * 128 + lane * 4]) = acc;
+    if (lane == 0) {
+      cm_ml[(warp * D8_ROWS + r) * 2] = mm;
+      cm_ml[(warp * D8_ROWS + r) * 2 + 1] = ll;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rows_total * 64; idx += I4_THREADS) {
+    const int r = idx >> 6, d = (idx & 63) * 2;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) mm = fmaxf(mm, cm_ml[(w * D8_ROWS + r) * 2]);
+    float a0f = 0.f, a1f = 0.f, ll = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = cm_ml[(w * D8_ROWS + r) * 2];
+      if (mw == -INFINITY) continue;
+      const float f = fast_exp2(mw - mm);
+      a0f += f * cm_o[(w * D8_ROWS + r) * 128 + d];
+      a1f += f * cm_o[(w * D8_ROWS + r) * 128 + d + 1];
+      ll += f * cm_ml[(w * D8_ROWS + r) * 2 + 1];
+    }
+    const float inv = ll > 0.f ? 1.f / ll : 0.f;
+    store_row_elem(r, d, a0f * inv, a1f * inv);
+  }
+  if (tid == 0) p.counters[item] = 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 int stage_offset(const duo_layer_desc& d);  // api.cu
 
@@ -664,8 +1180,119 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
   return DUO_OK;
 }
 
+// EXPERIMENTAL launch of duo_attn_int4_dec8_kernel (group * q_len <= 8): 4 CTAs / SM, 8-row split-KV workspace.
+static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride,
+                          void* out, int q_len, float scale, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream) {
+  const duo_layer_desc& d = L->d;
+  I4Params p{};
+  p.q = q;
+  p.out = out;
+  p.q_tok_stride = q_row_stride;
+  p.q_batch_stride = q_row_stride * q_len;
+  const int n_q = (d.n_full + d.n_stream) * d.group;
+  p.out_batch_stride = (long long)q_len * n_q * kHeadDim;
+  p.q_len = q_len;
+  p.n_q_heads = n_q;
+  p.group = d.group;
+  p.n_full = d.n_full;
+  p.n_stream = d.n_stream;
+  p.batch = d.batch;
+  p.sink = d.sink;
+  p.recent = d.recent;
+  p.W = d.sink + d.recent;
+  p.stage_off = stage_offset(d);
+  p.full_len = st->full_len;
+  p.total = st->total;
+  p.lo = st->lo;
+  p.dstate = reinterpret_cast<const long long*>(st->device_state);
+  p.full_cap = d.full_cap;
+  p.ring_slots = (long long)p.stage_off + d.stage_cap;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.n_rb = 1;
+  p.cache_scan = (int)std::min<long long>(p.W, st->total);
+  p.full_k = (const uint8_t*)d.full_k;
+  p.full_v = (const uint8_t*)d.full_v;
+  p.ring_k = (const uint8_t*)d.ring_k;
+  p.ring_v = (const uint8_t*)d.ring_v;
+  p.fks = (const __half*)d.full_k_scale;
+  p.fkz = (const __half*)d.full_k_zero;
+  p.fvs = (const __half*)d.full_v_scale;
+  p.fvz = (const __half*)d.full_v_zero;
+  p.rks = (const __half*)d.ring_k_scale;
+  p.rkz = (const __half*)d.ring_k_zero;
+  p.rvs = (const __half*)d.ring_v_scale;
+  p.rvz = (const __half*)d.ring_v_zero;
+
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int cached_dev = -1, cached_sms = 148;
+    if (cached_dev != dev) {
+      cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+      cached_dev = dev;
+    }
+    sm_count = cached_sms;
+  }
+  const long long nkeys = st->full_len + q_len;
+  int splits = 1;
+  if (d.n_full > 0) {
+    const int budget = 4 * sm_count;  // 4 resident CTAs per SM
+    const int base_ctas = d.batch * d.n_full;
+    const int stream_ctas = d.batch * d.n_stream;
+    int want = (budget - stream_ctas > 0 ? budget - stream_ctas : 1) / base_ctas;
+    if (want < 1) want = 1;
+    const long long max_by_len = (nkeys + 8 * D8_TILE - 1) / (8 * D8_TILE);  // >= 1024 keys per split
+    splits = (int)std::min<long long>(want, std::max<long long>(1, max_by_len));
+    if (splits > 512) splits = 512;
+  }
+  long long kps = (nkeys + splits - 1) / splits;
+  kps = (kps + D8_TILE - 1) / D8_TILE * D8_TILE;
+  if (kps < D8_TILE) kps = D8_TILE;
+  splits = (int)((nkeys + kps - 1) / kps);
+  if (splits < 1) splits = 1;
+  p.splits_full = splits;
+  p.keys_per_split = (int)kps;
+  const long long items = (long long)d.batch * d.n_full;
+  const size_t need_o = (size_t)items * splits * D8_ROWS * 128 * 4;
+  const size_t need_ml = (size_t)items * splits * D8_ROWS * 2 * 4;
+  const size_t need_cnt = (size_t)(items + 1) * 4;
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < need_o + need_ml + need_cnt + 1024)) {
+    set_error("duo_attention(int4/dec8): workspace too small (%zu < %zu)", workspace_bytes,
+              need_o + need_ml + need_cnt + 1024);
+    return DUO_EWORKSPACE;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  p.counters = reinterpret_cast<int*>(ws);
+  const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
+  p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
+  p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
+  const int grid_x = d.n_full * splits + d.n_stream;
+  if (grid_x == 0) return DUO_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DUO_CUDA_TRY(cudaFuncSetAttribute(duo_attn_int4_dec8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      D8_SMEM_BYTES));
+    attr_set = true;
+  }
+  duo_attn_int4_dec8_kernel<<<dim3(grid_x, d.batch), I4_THREADS, D8_SMEM_BYTES, stream>>>(p);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+static bool swapab_enabled() {  // experimental kernel: opt-in until it has been validated on hardware
+  static const bool on = [] {
+    const char* e = getenv("DUO_INT4_SWAPAB");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 int launch_attn_int4(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
                      int q_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (L->d.group * q_len <= D8_ROWS && swapab_enabled())
+    return launch_i4_dec8(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
   if (L->d.group * q_len <= 16)
     return launch_i4<4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
   return launch_i4<1>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);

@@ -1,0 +1,317 @@
+"""Lane-level CPU emulation of the fragment algebra of ``duo_attn_int4_dec8_kernel`` (attn_int4.cu, the
+experimental "keys are M" INT4 decode kernel).
+
+No GPU is involved: the warp-level instructions the kernel uses are emulated from their PTX-ISA register layouts
+(mma.sync.m16n8k16 A/B/C fragments, ldmatrix.x4.trans, movmatrix.trans, the (w & mask) | 0x6400 nibble -> fp16 trick)
+and the kernel body is replayed for one warp, register by register, in the same order as the CUDA source.  The result
+is compared with a direct float64 evaluation of attention over the dequantised keys.  This pins down every index
+mapping in the kernel (which nibble lands in which k-slot, the Q^T permutation and the 1/16 pre-scale, the +1024
+offset removal through the constant-one MMA, the S^T -> P'^T transposition, the head_dim order of the O^T tiles, the
+lazy running-max update); it does not replace the hardware parity run (DUO_INT4_SWAPAB=1 pytest -m gpu)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+F = np.float32
+LANES = range(32)
+
+
+def h2(w):
+    """u32 -> the two fp16 values it holds (lo, hi) as float32."""
+    return np.array([w & 0xFFFF, (w >> 16) & 0xFFFF], dtype=np.uint16).view(np.float16).astype(F)
+
+
+def pack_h2(lo, hi):
+    v = np.array([lo, hi], dtype=F).astype(np.float16).view(np.uint16)
+    return int(v[0]) | (int(v[1]) << 16)
+
+
+def lop_lo(w):
+    return (w & 0x000F000F) | 0x64006400
+
+
+def lop_hi(w):
+    return (w & 0x00F000F0) | 0x64006400
+
+
+def mma_16816(c, a, b):
+    """c[lane][4] += A(16x16) . B(16x8) with the m16n8k16 f16 fragment layouts of the PTX ISA."""
+    A = np.zeros((16, 16), F)
+    B = np.zeros((16, 8), F)
+    for lane in LANES:
+        g, t = lane >> 2, lane & 3
+        for reg, (dr, dc) in enumerate(((0, 0), (8, 0), (0, 8), (8, 8))):
+            A[g + dr, 2 * t + dc: 2 * t + dc + 2] = h2(a[lane][reg])
+        for reg, dk in enumerate((0, 8)):
+            B[2 * t + dk: 2 * t + dk + 2, g] = h2(b[lane][reg])
+    D = (A.astype(np.float64) @ B.astype(np.float64)).astype(F)
+    for lane in LANES:
+        g, t = lane >> 2, lane & 3
+        c[lane][0] += D[g, 2 * t]
+        c[lane][1] += D[g, 2 * t + 1]
+        c[lane][2] += D[g + 8, 2 * t]
+        c[lane][3] += D[g + 8, 2 * t + 1]
+
+
+def movm_trans(vals):
+    """movmatrix.sync.aligned.m8n8.trans.b16: lane (g,t) holds row g, elements 2t, 2t+1."""
+    M = np.zeros((8, 8), np.uint16)
+    for lane in LANES:
+        g, t = lane >> 2, lane & 3
+        M[g, 2 * t] = vals[lane] & 0xFFFF
+        M[g, 2 * t + 1] = vals[lane] >> 16
+    T = M.T
+    return [int(T[lane >> 2, 2 * (lane & 3)]) | (int(T[lane >> 2, 2 * (lane & 3) + 1]) << 16) for lane in LANES]
+
+
+def ldsm_x4_trans(smem, addrs):
+    """ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16: lanes 8m..8m+7 give the row addresses of matrix m."""
+    out = [[0] * 4 for _ in LANES]
+    for m in range(4):
+        M = np.zeros((8, 8), np.uint16)
+        for r in range(8):
+            M[r] = smem[addrs[8 * m + r]: addrs[8 * m + r] + 16].view(np.uint16)
+        for lane in LANES:
+            g, t = lane >> 2, lane & 3
+            out[lane][m] = int(M[2 * t, g]) | (int(M[2 * t + 1, g]) << 16)
+    return out
+
+
+def tile_image(packed):
+    """[keys][64] packed bytes -> the swizzled shared-memory image written by the loader (16 B chunk c of row r at
+    r*64 + ((c ^ ((r>>1)&3)) << 4))."""
+    n = packed.shape[0]
+    img = np.zeros(n * 64, np.uint8)
+    for r in range(n):
+        for c in range(4):
+            off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4)
+            img[off: off + 16] = packed[r, 16 * c: 16 * c + 16]
+    return img
+
+
+def emulate_warp(q, kp, ks, kz, vp, vs, vz, group, scale_log2, base, key0=0, visible=None):
+    """One warp of duo_attn_int4_dec8_kernel over consecutive 32-key tiles of its own.
+    q [rows<=8,128] fp16; kp/vp [n,64] u8; ks.. [n] fp16; visible[row][key] bool or None.
+    Returns (O un-normalised [8,128], m [8] (log2 domain), l [8])."""
+    rows_total = q.shape[0]
+    n = kp.shape[0]
+    assert n % 32 == 0
+    q16 = np.zeros((8, 128), np.float16)
+    q16[:rows_total] = q
+    # ---- Q^T B fragments (lane = (row g, chunk t4)) + qsum / qoff ----
+    qb = [[[0, 0] for _ in range(8)] for _ in LANES]
+    s_all = np.zeros(32, F)
+    s_off = np.zeros(32, F)
+    for lane in LANES:
+        g, t4 = lane >> 2, lane & 3
+        for w in range(4):
+            e = q16[g, 32 * t4 + 8 * w: 32 * t4 + 8 * w + 8]
+            h = (e.astype(np.float16) * np.float16(0.0625)).astype(np.float16)
+            qb[lane][2 * w][0] = pack_h2(e[1], e[5])
+            qb[lane][2 * w][1] = pack_h2(h[0], h[4])
+            qb[lane][2 * w + 1][0] = pack_h2(e[3], e[7])
+            qb[lane][2 * w + 1][1] = pack_h2(h[2], h[6])
+            s_all[lane] += e.astype(F).sum()
+            s_off[lane] += F(1024.0) * (F(e[1]) + F(e[5]) + F(e[3]) + F(e[7]) + F(h[0]) + F(h[4]) + F(h[2]) + F(h[6]))
+    for arr in (s_all, s_off):  # xor-1, xor-2 butterflies
+        arr[:] = [arr[(lane & ~3)] + arr[(lane & ~3) + 1] + arr[(lane & ~3) + 2] + arr[(lane & ~3) + 3] for lane in LANES]
+    qsum = [[s_all[(2 * (lane & 3) + e) * 4] for e in range(2)] for lane in LANES]
+    qoff = [[s_off[(2 * (lane & 3) + e) * 4] for e in range(2)] for lane in LANES]
+
+    oT = [[[F(0)] * 4 for _ in range(8)] for _ in LANES]
+    psT = [[F(0)] * 4 for _ in LANES]
+    m_run = [[F(-np.inf)] * 2 for _ in LANES]
+    l_run = [[F(0)] * 2 for _ in LANES]
+    pz_run = [[F(0)] * 2 for _ in LANES]
+    ones = [[0x3C003C00] * 4 for _ in LANES]
+
+    for tile in range(n // 32):
+        sl = slice(tile * 32, tile * 32 + 32)
+        sK, sV = tile_image(kp[sl]), tile_image(vp[sl])
+        tks, tkz, tvs, tvz = (a[sl].astype(F) for a in (ks, kz, vs, vz))
+        # ---- S^T raw ----
+        sc = [[[F(0)] * 4 for _ in range(2)] for _ in LANES]
+        for mt in range(2):
+            acc = [[F(0)] * 4 for _ in LANES]
+            words = []
+            for lane in LANES:
+                g, t4 = lane >> 2, lane & 3
+                k0, k1 = mt * 16 + g, mt * 16 + g + 8
+                a0 = k0 * 64 + ((t4 ^ ((k0 >> 1) & 3)) << 4)
+                a1 = k1 * 64 + ((t4 ^ ((k1 >> 1) & 3)) << 4)
+                words.append((sK[a0:a0 + 16].view(np.uint32), sK[a1:a1 + 16].view(np.uint32)))
+            for w in range(4):
+                for half in range(2):
+                    fa = []
+                    for lane in LANES:
+                        x, y = int(words[lane][0][w]), int(words[lane][1][w])
+                        if half:
+                            x, y = x >> 8, y >> 8
+                        fa.append([lop_lo(x), lop_lo(y), lop_hi(x), lop_hi(y)])
+                    mma_16816(acc, fa, [qb[lane][2 * w + half] for lane in LANES])
+            for lane in LANES:
+                sc[lane][mt] = acc[lane]
+        # ---- logits + mask ----
+        for lane in LANES:
+            g, t4 = lane >> 2, lane & 3
+            for mt in range(2):
+                for hk in range(2):
+                    key = mt * 16 + hk * 8 + g
+                    for e in range(2):
+                        v = tks[key] * (sc[lane][mt][hk * 2 + e] - qoff[lane][e]) + tkz[key] * qsum[lane][e]
+                        r = 2 * t4 + e
+                        j = key0 + tile * 32 + key
+                        ok = r < rows_total and j <= base + r // group
+                        if visible is not None and ok:
+                            ok = bool(visible[r][tile * 32 + key])
+                        sc[lane][mt][hk * 2 + e] = F(v) if ok else F(-np.inf)
+        # ---- lazy running max ----
+        mx = [[max(sc[lane][0][e], sc[lane][0][e + 2], sc[lane][1][e], sc[lane][1][e + 2]) for e in range(2)]
+              for lane in LANES]
+        moved = any(mx[lane][e] > m_run[lane][e] for lane in LANES for e in range(2))
+        if moved:
+            for e in range(2):
+                red = [max(mx[(gg << 2) | (lane & 3)][e] for gg in range(8)) for lane in LANES]
+                for lane in LANES:
+                    m_new = max(m_run[lane][e], red[lane])
+                    msn = F(0) if m_new == -np.inf else F(m_new * scale_log2)
+                    alpha = F(0) if m_run[lane][e] == -np.inf else F(np.exp2(F(m_run[lane][e] * scale_log2) - msn))
+                    m_run[lane][e] = m_new
+                    l_run[lane][e] *= alpha
+                    pz_run[lane][e] *= alpha
+                    psT[lane][e] *= alpha
+                    psT[lane][e + 2] *= alpha
+                    for d in range(8):
+                        oT[lane][d][e] *= alpha
+                        oT[lane][d][e + 2] *= alpha
+        # ---- exponentials, P' and its transposition ----
+        pb = [[[0, 0] for _ in range(2)] for _ in LANES]
+        for mt in range(2):
+            for hk in range(2):
+                packed = []
+                for lane in LANES:
+                    g = lane >> 2
+                    key = mt * 16 + hk * 8 + g
+                    pp = []
+                    for e in range(2):
+                        msc = F(0) if m_run[lane][e] == -np.inf else F(m_run[lane][e] * scale_log2)
+                        pv = F(np.exp2(F(sc[lane][mt][hk * 2 + e] * scale_log2) - msc))
+                        l_run[lane][e] += pv
+                        pz_run[lane][e] += pv * tvz[key]
+                        pp.append(pv * tvs[key])
+                    packed.append(pack_h2(pp[0], pp[1]))
+                tr = movm_trans(packed)
+                for lane in LANES:
+                    pb[lane][mt][hk] = tr[lane]
+        # ---- O^T raw ----
+        for k2 in range(2):
+            bfr = [pb[lane][k2] for lane in LANES]
+            mma_16816(psT, ones, bfr)
+            for call in range(2):
+                addrs = []
+                for lane in LANES:
+                    lrow, lmat = lane & 7, lane >> 3
+                    key = k2 * 16 + (lmat & 1) * 8 + lrow
+                    blk = 2 * call + (lmat >> 1)
+                    addrs.append(key * 64 + ((blk ^ ((key >> 1) & 3)) << 4))
+                r = ldsm_x4_trans(sV, addrs)
+                for ii, fn, sh in ((1, lop_lo, 0), (0, lop_hi, 0), (3, lop_lo, 8), (2, lop_hi, 8)):
+                    fa = [[fn(r[lane][0] >> sh), fn(r[lane][2] >> sh), fn(r[lane][1] >> sh), fn(r[lane][3] >> sh)]
+                          for lane in LANES]
+                    acc = [oT[lane][call * 4 + ii] for lane in LANES]
+                    mma_16816(acc, fa, bfr)
+    # ---- epilogue ----
+    O = np.zeros((8, 128), F)
+    m_out = np.full(8, -np.inf, F)
+    l_out = np.zeros(8, F)
+    for e in range(2):
+        for t4 in range(4):
+            r = 2 * t4 + e
+            l_out[r] = sum(l_run[(gg << 2) | t4][e] for gg in range(8))
+            pz = sum(pz_run[(gg << 2) | t4][e] for gg in range(8))
+            lane0 = t4
+            m_out[r] = m_run[lane0][e] * scale_log2 if m_run[lane0][e] != -np.inf else -np.inf
+            for g in range(8):
+                lane = (g << 2) | t4
+                off = F(1024.0) * psT[lane][e]
+                for tl in range(8):
+                    call, ii = tl >> 2, tl & 3
+                    mul = F(1.0) if ii & 1 else F(0.0625)
+                    for hm in range(2):
+                        d = 32 * (2 * call + hm) + 4 * g + ii
+                        O[r, d] = (oT[lane][tl][hm * 2 + e] - off) * mul + pz
+    return O, m_out, l_out
+
+
+def truth(q, kp, ks, kz, vp, vs, vz, group, scale, base, key0=0, visible=None):
+    from oracle.int4_oracle import unpack_codes
+
+    K = unpack_codes(kp).astype(np.float64) * ks.astype(np.float64)[:, None] + kz.astype(np.float64)[:, None]
+    V = unpack_codes(vp).astype(np.float64) * vs.astype(np.float64)[:, None] + vz.astype(np.float64)[:, None]
+    S = q.astype(np.float64) @ K.T * scale
+    n = kp.shape[0]
+    for r in range(q.shape[0]):
+        for j in range(n):
+            ok = key0 + j <= base + r // group
+            if visible is not None and ok:
+                ok = bool(visible[r][j])
+            if not ok:
+                S[r, j] = -np.inf
+    m = S.max(axis=1, keepdims=True)
+    P = np.exp(S - m)
+    return (P @ V) / P.sum(axis=1, keepdims=True)
+
+
+def _case(seed, n_keys, rows, group, big_first=False):
+    rng = np.random.default_rng(seed)
+    q = (rng.standard_normal((rows, 128)) * 1.5).astype(np.float16)
+    kp = rng.integers(0, 256, (n_keys, 64), dtype=np.uint8)
+    vp = rng.integers(0, 256, (n_keys, 64), dtype=np.uint8)
+    ks = rng.uniform(0.02, 0.3, n_keys).astype(np.float16)
+    kz = rng.uniform(-2.5, -0.2, n_keys).astype(np.float16)
+    vs = rng.uniform(0.02, 0.3, n_keys).astype(np.float16)
+    vz = rng.uniform(-2.5, -0.2, n_keys).astype(np.float16)
+    if big_first:  # make the running max settle in the first tile so later tiles take the no-rescale path
+        ks[:32] = np.float16(0.3)
+    return q, kp, ks, kz, vp, vs, vz
+
+
+@pytest.mark.parametrize("rows,group,n_keys", [(8, 4, 32), (4, 4, 64), (8, 1, 64), (2, 2, 96)])
+def test_swapab_fragment_algebra_matches_direct_attention(rows, group, n_keys):
+    q, kp, ks, kz, vp, vs, vz = _case(100 + rows + n_keys, n_keys, rows, group)
+    scale = 128 ** -0.5
+    base = 10 ** 9  # every key visible
+    O, m, l = emulate_warp(q, kp, ks, kz, vp, vs, vz, group, F(scale * 1.4426950408889634), base)
+    got = O[:rows] / l[:rows, None]
+    ref = truth(q, kp, ks, kz, vp, vs, vz, group, scale, base)
+    err = np.abs(got - ref).max()
+    assert err < 4e-3 * max(1.0, np.abs(ref).max()), err
+
+
+def test_swapab_causal_mask_and_lazy_rescale():
+    """q_len = 2 (group 4): the last key is visible to the second token only; keys beyond are masked for everyone.
+    The first tile holds the largest logits, so the following tiles exercise the 'max did not move' path."""
+    rows, group, n_keys = 8, 4, 64
+    q, kp, ks, kz, vp, vs, vz = _case(7, n_keys, rows, group, big_first=True)
+    scale = 128 ** -0.5
+    base = 58  # token 0 sees keys 0..58, token 1 sees 0..59; 60..63 are the zero-filled tail
+    O, m, l = emulate_warp(q, kp, ks, kz, vp, vs, vz, group, F(scale * 1.4426950408889634), base)
+    got = O / l[:, None]
+    ref = truth(q, kp, ks, kz, vp, vs, vz, group, scale, base)
+    assert np.abs(got - ref).max() < 4e-3 * max(1.0, np.abs(ref).max())
+    # rows of token 0 and token 1 really saw different key sets
+    ref_all = truth(q, kp, ks, kz, vp, vs, vz, group, scale, 10 ** 9)
+    assert np.abs(ref - ref_all).max() > 1e-3
+
+
+def test_swapab_fully_masked_rows_stay_empty():
+    rows, group, n_keys = 4, 4, 32
+    q, kp, ks, kz, vp, vs, vz = _case(9, n_keys, rows, group)
+    vis = np.zeros((rows, n_keys), bool)
+    vis[0, :5] = True  # only row 0 sees anything
+    O, m, l = emulate_warp(q, kp, ks, kz, vp, vs, vz, group, F(0.1), 10 ** 9, visible=vis)
+    assert l[0] > 0 and np.all(l[1:] == 0) and np.all(np.isneginf(m[1:]))
+    assert np.all(np.isfinite(O))
+    ref = truth(q[:1], kp, ks, kz, vp, vs, vz, group, 0.1 / 1.4426950408889634, 10 ** 9, visible=vis[:1])
+    assert np.abs(O[0] / l[0] - ref[0]).max() < 4e-3 * max(1.0, np.abs(ref).max())
