@@ -22,6 +22,7 @@ DECODE_MAX_Q = 16
 SYMBOLS = [
     "duo_layer_create", "duo_layer_destroy", "duo_workspace_bytes", "duo_rope_append", "duo_attention",
     "duo_attention_mma", "duo_state_advance", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
+    "duo_comm_data_bytes", "duo_comm_flag_bytes", "duo_comm_create", "duo_comm_destroy", "duo_allreduce_add_rmsnorm",
     "duo_last_error_string", "duo_version",
 ]
 
@@ -41,6 +42,12 @@ class LayerDesc(C.Structure):
 
 class CacheState(C.Structure):
     _fields_ = [("full_len", C.c_int64), ("total", C.c_int64), ("lo", C.c_int64), ("device_state", C.c_void_p)]
+
+
+class CommDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("local_state", C.c_void_p),
+                ("rank", C.c_int32), ("world", C.c_int32), ("hidden", C.c_int32), ("max_rows", C.c_int32),
+                ("dtype", C.c_int32)]
 
 
 _lib = None
@@ -82,6 +89,16 @@ def load():
     lib.duo_add_rmsnorm.restype = C.c_int
     lib.duo_silu_mul.argtypes = [vp, vp, i64, i32, i32, vp]
     lib.duo_silu_mul.restype = C.c_int
+    lib.duo_comm_data_bytes.argtypes = [i32, i32, i32, i32]
+    lib.duo_comm_data_bytes.restype = sz
+    lib.duo_comm_flag_bytes.argtypes = [i32, i32]
+    lib.duo_comm_flag_bytes.restype = sz
+    lib.duo_comm_create.argtypes = [C.POINTER(CommDesc), C.POINTER(vp)]
+    lib.duo_comm_create.restype = C.c_int
+    lib.duo_comm_destroy.argtypes = [vp]
+    lib.duo_comm_destroy.restype = None
+    lib.duo_allreduce_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, f32, vp]
+    lib.duo_allreduce_add_rmsnorm.restype = C.c_int
     lib.duo_last_error_string.argtypes = []
     lib.duo_last_error_string.restype = C.c_char_p
     lib.duo_version.argtypes = []

@@ -144,22 +144,36 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
         # fused glue: residual add + RMSNorm in one launch, gate|up in one GEMM, SiLU*up in one launch
         from .. import ops
 
+        comm = getattr(self, "_duo_comm", None) if tp_on else None
+        if comm is not None and not comm.usable(h):
+            comm = None  # large chunks are bandwidth-bound: NCCL
+
+        def reduce_add_norm(part, res, w, eps):
+            """sum over ranks (if TP) + residual add + RMSNorm: one fused peer-memory kernel for small exchanges
+            (experimental, DUO_FUSED_ALLREDUCE=1), otherwise NCCL all-reduce followed by duo_add_rmsnorm."""
+            if comm is not None:
+                return comm.add_rmsnorm(part, res, w, eps)
+            if tp_on:  # row-parallel partials -> one all-reduce per site (NCCL over NVLink)
+                part = all_reduce_sum(part, self._duo_tp_group)
+            return ops.add_rmsnorm(part, res, w, eps)
+
         x, _ = ops.add_rmsnorm(h, None, layers[0].input_layernorm.weight, layers[0].input_layernorm.variance_epsilon)
         for idx, layer in enumerate(layers):
             a = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
-            if tp_on:  # row-parallel o_proj partials -> one all-reduce per layer (NCCL over NVLink)
-                a = all_reduce_sum(a, self._duo_tp_group)
             ln2 = layer.post_attention_layernorm
-            x, h = ops.add_rmsnorm(a, h, ln2.weight, ln2.variance_epsilon)
+            x, h = reduce_add_norm(a, h, ln2.weight, ln2.variance_epsilon)
             m = _mlp_forward(layer.mlp, x)
-            if tp_on:
-                m = all_reduce_sum(m, self._duo_tp_group)
             if idx + 1 < len(layers):
                 nxt = layers[idx + 1].input_layernorm
-                x, h = ops.add_rmsnorm(m, h, nxt.weight, nxt.variance_epsilon)
+                x, h = reduce_add_norm(m, h, nxt.weight, nxt.variance_epsilon)
             else:  # only the last position feeds the head (tuple_kv_cache.py:283-288)
-                x, _ = ops.add_rmsnorm(m[:, -1:, :].contiguous(), h[:, -1:, :].contiguous(), base.norm.weight,
-                                       base.norm.variance_epsilon)
+                if tp_on and comm is None:
+                    m = all_reduce_sum(m, self._duo_tp_group)
+                m_last, h_last = m[:, -1:, :].contiguous(), h[:, -1:, :].contiguous()
+                if comm is not None:
+                    x, _ = comm.add_rmsnorm(m_last, h_last, base.norm.weight, base.norm.variance_epsilon)
+                else:
+                    x, _ = ops.add_rmsnorm(m_last, h_last, base.norm.weight, base.norm.variance_epsilon)
         h = x
     else:
         for idx, layer in enumerate(layers):

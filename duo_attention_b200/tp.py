@@ -81,11 +81,100 @@ def all_reduce_sum(x: torch.Tensor, group=None) -> torch.Tensor:
     return x
 
 
+class FusedAllReduce:
+    """EXPERIMENTAL peer-memory communicator for ``duo_allreduce_add_rmsnorm`` (csrc/comm.cu): the latency-bound
+    exchanges (decode, chunks of <= ``max_rows`` tokens) become one kernel that pushes the partial row to every
+    rank over NVLink, sums in rank order and applies the residual add + RMSNorm that follows.
+
+    PyTorch only provides the plumbing here: a symmetric-memory allocation whose peer mappings
+    (``buffer_ptrs``) are handed to the C ABI.  Larger chunks keep using NCCL (``all_reduce_sum``)."""
+
+    def __init__(self, group, hidden: int, dtype: torch.dtype, device, max_rows: int = 16):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _C
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if not 2 <= self.world <= 8:
+            raise ValueError(f"FusedAllReduce supports 2..8 ranks, got {self.world}")
+        self.hidden, self.max_rows, self.dtype = int(hidden), int(max_rows), dtype
+        dt = _C.DT_BF16 if dtype == torch.bfloat16 else _C.DT_FP16
+        lib = _C.load()
+        data_bytes = lib.duo_comm_data_bytes(self.world, self.hidden, self.max_rows, dt)
+        flag_bytes = lib.duo_comm_flag_bytes(self.world, self.max_rows)
+        try:  # older torch needs the group enabled explicitly; newer versions do it inside rendezvous
+            symm.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.buf = symm.empty(data_bytes + flag_bytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.state = torch.zeros(self.max_rows + 1, dtype=torch.int32, device=device)
+        desc = _C.CommDesc()
+        ptrs = list(self.handle.buffer_ptrs)
+        for r in range(self.world):
+            desc.data[r] = ptrs[r]
+            desc.flags[r] = ptrs[r] + data_bytes
+        desc.local_state = self.state.data_ptr()
+        desc.rank, desc.world, desc.hidden, desc.max_rows, desc.dtype = self.rank, self.world, self.hidden, self.max_rows, dt
+        out = C.c_void_p()
+        _C.check(lib.duo_comm_create(C.byref(desc), C.byref(out)))
+        self._h = out
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)  # every rank has zeroed its buffers before anyone pushes into them
+
+    def usable(self, x: torch.Tensor) -> bool:
+        return x.numel() // x.shape[-1] <= self.max_rows and x.shape[-1] == self.hidden and x.dtype == self.dtype
+
+    def add_rmsnorm(self, partial: torch.Tensor, residual, weight: torch.Tensor, eps: float):
+        """``h = residual + sum_ranks(partial)`` (in place in ``residual`` if given) -> ``(rmsnorm(h) * weight, h)``."""
+        from . import _C, ops
+
+        partial = partial if partial.is_contiguous() else partial.contiguous()
+        rows = partial.numel() // self.hidden
+        out = torch.empty_like(partial)
+        if residual is not None:
+            assert residual.is_contiguous() and residual.shape == partial.shape and residual.dtype == partial.dtype
+            h = residual
+        else:
+            h = torch.empty_like(partial)
+        _C.check(_C.load().duo_allreduce_add_rmsnorm(
+            self._h, partial.data_ptr(), None if residual is None else residual.data_ptr(), weight.data_ptr(),
+            out.data_ptr(), h.data_ptr(), rows, float(eps), torch.cuda.current_stream(partial.device).cuda_stream))
+        ops.LAUNCHES += 1
+        return out, h
+
+    def error(self) -> bool:
+        """True if some call timed out waiting for a peer (synchronises)."""
+        return bool(self.state[self.max_rows].item())
+
+    def __del__(self):
+        try:
+            from . import _C
+
+            if getattr(self, "_h", None):
+                _C.load().duo_comm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 def install_allreduce(model, group=None):
     """Mark a patched (enable_duo_attention_eval) per-rank model shard as tensor-parallel: the driver then
-    all-reduces the attention and MLP outputs of every layer."""
+    all-reduces the attention and MLP outputs of every layer (NCCL).  With ``DUO_FUSED_ALLREDUCE=1`` in the
+    environment (experimental) exchanges of <= 16 rows go through ``FusedAllReduce`` instead."""
+    import os
+
     model._duo_tp_group = group
     model._duo_tp = True
+    model._duo_comm = None
+    if os.environ.get("DUO_FUSED_ALLREDUCE") == "1" and dist.is_initialized() and dist.get_world_size(group) > 1:
+        p = next(model.parameters())
+        if p.is_cuda:
+            model._duo_comm = FusedAllReduce(group, model.config.hidden_size, p.dtype, p.device)
     return model
 
 

@@ -204,6 +204,38 @@ DUO_API int duo_add_rmsnorm(const void* x, const void* residual, const void* wei
                             int64_t rows, int32_t hidden, float eps, int32_t dtype, void* stream);
 DUO_API int duo_silu_mul(const void* gate_up, void* out, int64_t rows, int32_t inter, int32_t dtype, void* stream);
 
+/*
+ * EXPERIMENTAL (head-parallel TP): the per-layer exchange step of the reference's
+ * tensor-parallel sharding (duo_attn/utils.py:174-176, "sum" of the row-parallel o_proj / down_proj partials) as a
+ * one-shot all-reduce over NVLink peer memory, fused with the residual add + RMSNorm that consumes it:
+ *   out_res  = T( T(sum over ranks of partial) + residual )         (residual may be NULL: no add)
+ *   out_norm = weight * T( out_res_fp32 * rsqrt(mean(out_res_fp32^2) + eps) )
+ * rows <= max_rows (decode and small chunks; latency-bound sizes).  The caller owns all memory:
+ *   data[r]  : rank r's receive buffer, duo_comm_data_bytes() bytes, zero-initialised, mapped on EVERY rank
+ *              (CUDA IPC / torch symmetric memory; data[rank] is the local one); 16-byte aligned
+ *   flags[r] : rank r's flag words, duo_comm_flag_bytes() bytes, zero-initialised, mapped on every rank
+ *   local_state : local device int32[max_rows + 1], zero-initialised (call epochs; last word = error flag,
+ *              set to 1 if a peer did not arrive within ~3 s - the result of that call is then undefined)
+ * Every rank must issue the same sequence of calls (same rows) on one stream each.  Graph-capturable.
+ */
+typedef struct duo_comm duo_comm;
+typedef struct duo_comm_desc {
+  void* data[8];
+  void* flags[8];
+  void* local_state;
+  int32_t rank, world;   /* 2 <= world <= 8 */
+  int32_t hidden;        /* row length in elements, multiple of 8, <= 16384 */
+  int32_t max_rows;      /* <= 64 */
+  int32_t dtype;         /* DUO_DT_* */
+} duo_comm_desc;
+DUO_API size_t duo_comm_data_bytes(int32_t world, int32_t hidden, int32_t max_rows, int32_t dtype);
+DUO_API size_t duo_comm_flag_bytes(int32_t world, int32_t max_rows);
+DUO_API int duo_comm_create(const duo_comm_desc* desc, duo_comm** out);
+DUO_API void duo_comm_destroy(duo_comm* comm);
+DUO_API int duo_allreduce_add_rmsnorm(const duo_comm* comm, const void* partial, const void* residual,
+                                      const void* weight, void* out_norm, void* out_res, int32_t rows, float eps,
+                                      void* stream);
+
 DUO_API const char* duo_last_error_string(void);
 DUO_API int duo_version(void);
 

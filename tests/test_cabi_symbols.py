@@ -65,3 +65,27 @@ def test_sass_has_tma_and_tensor_core_instructions():
     # tcgen05.ld / tcgen05.st, cp.async (INT4 tiles) and the mma.sync used by the HBM-bound decode kernel
     for mnemonic in ("UTMALDG", "UTCHMMA", "LDTM", "STTM", "LDGSTS", "HMMA", "SYNCS", "UTCBAR"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS of libduo_b200.so"
+
+
+def test_comm_entry_points_validate_before_touching_cuda():
+    """duo_comm_* (experimental fused all-reduce): sizes and argument validation are host-only."""
+    import ctypes as C
+
+    _C = _ensure_built()
+    lib = _C.load()
+    assert lib.duo_comm_data_bytes(8, 4096, 16, _C.DT_BF16) == 2 * 8 * 16 * 4096 * 2
+    assert lib.duo_comm_flag_bytes(8, 16) == 512
+    assert lib.duo_comm_data_bytes(2, 4096, 16, 7) == 0  # unknown dtype
+    out = C.c_void_p()
+    d = _C.CommDesc()
+    d.rank, d.world, d.hidden, d.max_rows, d.dtype = 0, 1, 4096, 16, _C.DT_BF16
+    assert lib.duo_comm_create(C.byref(d), C.byref(out)) == _C.DUO_EINVAL  # world < 2
+    d.world = 2
+    d.local_state = 0x1000
+    assert lib.duo_comm_create(C.byref(d), C.byref(out)) == _C.DUO_EINVAL and "peer buffer 0" in _C.last_error()
+    d.data[0], d.data[1], d.flags[0], d.flags[1] = 0x10000, 0x20000, 0x30000, 0x40008
+    assert lib.duo_comm_create(C.byref(d), C.byref(out)) == _C.DUO_OK
+    rc = lib.duo_allreduce_add_rmsnorm(out, 0x100, None, 0x100, 0x100, None, 17, 1e-5, None)
+    assert rc == _C.DUO_EOVERFLOW and "max_rows 16" in _C.last_error()
+    assert lib.duo_allreduce_add_rmsnorm(out, None, None, None, None, None, 0, 1e-5, None) == _C.DUO_OK
+    lib.duo_comm_destroy(out)
