@@ -10,6 +10,14 @@
 
 namespace duo {
 
+bool wide_merge_enabled() {  // experimental split-KV merge variant, opt-in until validated on hardware
+  static const bool on = [] {
+    const char* e = getenv("DUO_WIDE_MERGE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {

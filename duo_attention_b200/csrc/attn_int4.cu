@@ -1018,39 +1018,20 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
   const float* pml = p.ws_ml + item * p.splits_full * (long long)(D8_ROWS * 2);
   float* cm_o = w_o;    // [4 warps][8 rows][128]
   float* cm_ml = w_ml;  // [4 warps][8 rows][2]
-  for (int r = 0; r < rows_total; ++r) {
-    float mm = -INFINITY, ll = 0.f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = warp; s0 < p.splits_full; s0 += 16) {
-      float ms[4], ls[4];
-      float4 vs[4];
+  for (int r0 = 0; r0 < rows_total; r0 += 4) {  // four rows per pass: 16 loads in flight (split_merge_rows4)
+    const int nr = min(4, rows_total - r0);
+    float4 acc4[4];
+    float mm4[4], ll4[4];
+    split_merge_rows4<D8_ROWS>(po, pml, p.splits_full, warp, lane, r0, nr, acc4, mm4, ll4);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int s2 = s0 + 4 * u;
-        const bool ok = s2 < p.splits_full;
-        const int sc2 = ok ? s2 : s0;
-        ms[u] = ok ? __ldcg(&pml[(sc2 * D8_ROWS + r) * 2]) : -INFINITY;
-        ls[u] = __ldcg(&pml[(sc2 * D8_ROWS + r) * 2 + 1]);
-        vs[u] = __ldcg(reinterpret_cast<const float4*>(&po[((long long)sc2 * D8_ROWS + r) * 128 + lane * 4]));
+    for (int q = 0; q < 4; ++q) {
+      if (q < nr) {
+        *reinterpret_cast<float4*>(&cm_o[(warp * D8_ROWS + r0 + q) * 128 + lane * 4]) = acc4[q];
+        if (lane == 0) {
+          cm_ml[(warp * D8_ROWS + r0 + q) * 2] = mm4[q];
+          cm_ml[(warp * D8_ROWS + r0 + q) * 2 + 1] = ll4[q];
+        }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (ms[u] == -INFINITY) continue;
-        const float mn = fmaxf(mm, ms[u]);
-        const float fo = (mm == -INFINITY) ? 0.f : fast_exp2(mm - mn);
-        const float fn = fast_exp2(ms[u] - mn);
-        acc.x = acc.x * fo + vs[u].x * fn;
-        acc.y = acc.y * fo + vs[u].y * fn;
-        acc.z = acc.z * fo + vs[u].z * fn;
-        acc.w = acc.w * fo + vs[u].w * fn;
-        ll = ll * fo + ls[u] * fn;
-        mm = mn;
-      }
-    }
-    *reinterpret_cast<float4*>(&cm_o[(warp * D8_ROWS + r) * 128 + lane * 4]) = acc;
-    if (lane == 0) {
-      cm_ml[(warp * D8_ROWS + r) * 2] = mm;
-      cm_ml[(warp * D8_ROWS + r) * 2 + 1] = ll;
     }
   }
   __syncthreads();

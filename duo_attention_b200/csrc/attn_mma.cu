@@ -45,6 +45,7 @@ struct AttnParams {
   float* ws_o;           // [batch][n_full][n_rb][splits][ROWS][128]
   float* ws_ml;          // [batch][n_full][n_rb][splits][ROWS][2]
   int* counters;         // [batch][n_full][n_rb]
+  int wide_merge;        // experimental: split_merge_rows4 in the last-CTA merge
 };
 
 template <typename T, int KEY_WARPS>
@@ -420,6 +421,24 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
   float* cm_ml = reinterpret_cast<float*>(smem + 80 * 1024);  // [4 warps][16][2]
   for (int rg = 0; rg < rows_here; rg += 16) {
   const int rg_n = min(16, rows_here - rg);
+  if (p.wide_merge) {
+    for (int rr0 = 0; rr0 < rg_n; rr0 += 4) {
+      const int nr = min(4, rg_n - rr0);
+      float4 acc4[4];
+      float mm4[4], ll4[4];
+      split_merge_rows4<ROWS>(po, pml, p.splits_full, warp, lane, rg + rr0, nr, acc4, mm4, ll4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < nr) {
+          *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr0 + q) * 128 + lane * 4]) = acc4[q];
+          if (lane == 0) {
+            cm_ml[(warp * 16 + rr0 + q) * 2] = mm4[q];
+            cm_ml[(warp * 16 + rr0 + q) * 2 + 1] = ll4[q];
+          }
+        }
+      }
+    }
+  } else
   for (int rr = 0; rr < rg_n; ++rr) {
     const int r = rg + rr;
     float mm = -INFINITY, ll = 0.f;
@@ -577,6 +596,7 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
   p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
   p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
+  p.wide_merge = wide_merge_enabled() ? 1 : 0;
 
   const int grid_x = d.n_full * p.n_rb * splits + d.n_stream * p.n_rb;
   if (grid_x == 0) return DUO_OK;

@@ -174,4 +174,57 @@ __device__ __forceinline__ bool stream_slot_valid(int j, int sink, int recent, l
   return p >= lo;
 }
 
+// Split-KV merge, wide variant (EXPERIMENTAL, DUO_WIDE_MERGE=1): one warp merges its share of the `splits` partials
+// (splits warp, warp+4, ...) for up to FOUR rows at once, i.e. 16 independent 512-byte loads in flight per iteration
+// instead of 4.  The row-at-a-time loop costs splits/16 dependent L2 round trips PER ROW, which dominates a
+// decode launch that has a single retrieval head (~290 splits: ~25 us of a ~75 us kernel).
+//   po  : [splits][ROWS][128] un-normalised partial outputs, pml : [splits][ROWS][2] (max in log2 domain, sum)
+//   rows r0 .. r0+nr-1 (nr <= 4); results: acc[q] (this lane's 4 output dims), mm[q], ll[q]
+template <int ROWS>
+__device__ __forceinline__ void split_merge_rows4(const float* po, const float* pml, int splits, int warp, int lane,
+                                                  int r0, int nr, float4 (&acc)[4], float (&mm)[4], float (&ll)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    mm[q] = -INFINITY;
+    ll[q] = 0.f;
+  }
+  for (int s0 = warp; s0 < splits; s0 += 16) {
+    float ms[4][4], ls[4][4];
+    float4 vs[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int s2 = s0 + 4 * u;
+      const bool sok = s2 < splits;
+      const int sc2 = sok ? s2 : s0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool ok = sok && q < nr;
+        const int r = r0 + (q < nr ? q : 0);
+        ms[u][q] = ok ? __ldcg(&pml[(sc2 * ROWS + r) * 2]) : -INFINITY;
+        ls[u][q] = __ldcg(&pml[(sc2 * ROWS + r) * 2 + 1]);
+        vs[u][q] = __ldcg(reinterpret_cast<const float4*>(&po[((long long)sc2 * ROWS + r) * 128 + lane * 4]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (ms[u][q] == -INFINITY) continue;
+        const float mn = fmaxf(mm[q], ms[u][q]);
+        const float fo = (mm[q] == -INFINITY) ? 0.f : fast_exp2(mm[q] - mn);
+        const float fn = fast_exp2(ms[u][q] - mn);
+        acc[q].x = acc[q].x * fo + vs[u][q].x * fn;
+        acc[q].y = acc[q].y * fo + vs[u][q].y * fn;
+        acc[q].z = acc[q].z * fo + vs[u][q].z * fn;
+        acc[q].w = acc[q].w * fo + vs[u][q].w * fn;
+        ll[q] = ll[q] * fo + ls[u][q] * fn;
+        mm[q] = mn;
+      }
+    }
+  }
+}
+
+bool wide_merge_enabled();  // api.cu: DUO_WIDE_MERGE=1
+
 }  // namespace duo
