@@ -12,6 +12,8 @@ device tensor, so ONE captured step can be replayed for every generated token:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 
@@ -20,7 +22,7 @@ class DuoDecodeGraph:
         if cache.growable:
             raise ValueError("DuoDecodeGraph needs a pre-allocated cache (DuoAttentionStaticKVCache): a growable "
                              "cache may be re-allocated, which would leave stale pointers in the captured graph")
-        if cache.kv_format != "same":
+        if cache.kv_format != "same" and os.environ.get("DUO_EXPERIMENTAL") != "1":
             raise ValueError("DuoDecodeGraph: INT4 caches are driven eagerly for now (the device-state path of the "
                              "INT4 kernel has not been validated on hardware yet)")
         self.model, self.cache = model, cache

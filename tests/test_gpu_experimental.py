@@ -1,0 +1,65 @@
+"""Hardware checks of the EXPERIMENTAL, opt-in code paths.  Skipped unless DUO_EXPERIMENTAL=1, and each path is only
+taken when its own switch is set in the environment of the test process:
+
+    DUO_EXPERIMENTAL=1 DUO_INT4_SWAPAB=1 DUO_WIDE_MERGE=1 python -m pytest tests/test_gpu_experimental.py -x -q
+
+(plus the regular suites under the same switches: tests/test_gpu_int4_attention.py, tests/test_gpu_attention.py,
+tests/test_gpu_model.py).  See profiles/validate_experimental.sh."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DUO_EXPERIMENTAL") != "1", reason="set DUO_EXPERIMENTAL=1")]
+
+
+def test_int4_many_splits():
+    """> 16 splits per retrieval head: the split-KV merge loop takes more than one pass per warp."""
+    from test_gpu_int4_attention import run
+
+    run(4, 1, 1, 64, 256, [20000, 1, 2, 1], seed=16, stage_cap=20000)
+
+
+def test_int4_batch2_decode():
+    from test_gpu_int4_attention import run
+
+    run(8, 2, 1, 8, 24, [3000, 1, 2, 1, 1], seed=17, B=2, stage_cap=3000)
+
+
+def test_int4_mha_rows_up_to_8():
+    """group 1: q_len 1..8 all fit the 8-row decode kernel."""
+    from test_gpu_int4_attention import run
+
+    run(4, 4, 2, 4, 12, [50, 1, 8, 7, 5, 1, 3], seed=18, stage_cap=50)
+
+
+def test_int4_cuda_graph_decode_matches_eager():
+    """Device-resident occupancy (dstate) path of the INT4 decode kernels: graph replay == eager, token by token."""
+    from duo_attention_b200.graph import DuoDecodeGraph
+    from duo_attn.patch import DuoAttentionStaticKVCache, enable_llama_duo_attention_static_kv_cache_eval
+    from test_gpu_model import tiny_model
+
+    model = tiny_model("llama", seed=7).to(torch.float16)
+    gates = np.array([[1.0, 0.0], [0.0, 1.0]])
+    sink, recent = 4, 6
+    enable_llama_duo_attention_static_kv_cache_eval(model, gates)
+    model.cuda()
+    ca = DuoAttentionStaticKVCache(model, gates, 1, 256, sink, recent, kv_format="int4")
+    cb = DuoAttentionStaticKVCache(model, gates, 1, 256, sink, recent, kv_format="int4")
+    g = torch.Generator().manual_seed(4)
+    ids = torch.randint(0, 512, (1, 37), generator=g).cuda()
+    with torch.no_grad():
+        model(input_ids=ids, past_key_values=ca, use_cache=True)
+        model(input_ids=ids, past_key_values=cb, use_cache=True)
+        graph = DuoDecodeGraph(model, cb)
+        toks = torch.randint(0, 512, (20, 1, 1), generator=g).cuda()
+        for i in range(20):
+            want = model(input_ids=toks[i], past_key_values=ca, use_cache=True).logits
+            got = graph.step(toks[i])
+            torch.testing.assert_close(got.float(), want.float(), rtol=0, atol=0, msg=lambda m: f"step {i}: {m}")
+            if i == 9:
+                ca.evict_last(1)
+                cb.evict_last(1)
+                graph.resync()
