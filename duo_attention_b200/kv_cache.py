@@ -21,6 +21,7 @@ object only owns buffers and three integers per layer; all data movement and mat
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -219,6 +220,67 @@ class DuoKVCache:
             self._scratch = sc
         return sc
 
+    # ---- EXPERIMENTAL (DUO_INT4_PREFILL_SCRATCH=1): large chunks over an INT4 cache on the tcgen05 kernel --------
+    def _dequant_scratch(self, l, S):
+        """fp16 image of layer ``l``'s INT4 cache for ONE attention call — literally what the reference does on every
+        call (``get()`` dequantises the whole cache, demo/int4_kv.py:373-436, then flash_attn_func runs on it,
+        demo/w8a8kv4_llama.py:239-274).  For a chunk of >= 128 tokens the O(ctx) dequantisation pass is noise next to
+        the chunk x ctx attention, and the attention then runs on the tensor-core prefill kernel instead of the
+        mma.sync INT4 kernel.  One flat fp16 buffer is shared by all layers (they are processed one after the other);
+        a layer handle is created per distinct number of retrieval heads."""
+        sc = self.__dict__.get("_dq")
+        B, D, Hkv = self.batch_size, self.head_dim, self.num_kv_heads
+        cap = max(self.full_cap_list)
+        slots = self.W + max(max(self.stage_cap_list), S)
+        if sc is None or sc["cap"] < cap or sc["slots"] < slots:
+            nf_max = max(self.num_full_kv_head_list)
+            ns_max = max(self.num_streaming_kv_head_list)
+            sc = {"cap": cap, "slots": slots, "handles": {},
+                  "full": [torch.empty(B * nf_max * cap * D, dtype=self.dtype, device=self.device) for _ in range(2)],
+                  "ring": [torch.empty(B * ns_max * slots * D, dtype=self.dtype, device=self.device) for _ in range(2)]}
+            old = self.__dict__.get("_dq")
+            if old is not None:
+                for hd in old["handles"].values():
+                    self.lib.duo_layer_destroy(hd)
+            self._dq = sc
+        nf, ns = self.num_full_kv_head_list[l], self.num_streaming_kv_head_list[l]
+        fk, fv = (t[: B * nf * cap * D].view(B, nf, cap, D) for t in sc["full"])
+        rk, rv = (t[: B * ns * slots * D].view(B, ns, slots, D) for t in sc["ring"])
+        if nf not in sc["handles"]:
+            d = _C.LayerDesc()
+            d.full_k, d.full_v = (fk.data_ptr(), fv.data_ptr()) if nf else (None, None)
+            d.ring_k, d.ring_v = (rk.data_ptr(), rv.data_ptr()) if ns else (None, None)
+            d.full_cap, d.batch, d.n_full, d.n_stream, d.group, d.head_dim = cap, B, nf, ns, self.num_kv_groups, D
+            d.sink, d.recent, d.stage_cap = self.sink_size, self.recent_size, slots - self.W
+            d.dtype = _C.DT_BF16 if self.dtype == torch.bfloat16 else _C.DT_FP16
+            d.kv_format = _C.KV_SAME
+            hd = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _C.check(self.lib.duo_layer_create(C.byref(d), C.byref(hd)))
+            sc["handles"][nf] = hd.value
+        # dequantise what this call can see: retrieval rows [0, full_len + S), sink + ring slots, the staged chunk
+        t = self.tensors[l]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        n_rows = self.kv_seq_len_list[l] + S
+        W, so = self.W, self.stage_off
+        n = 0
+        for b in range(B):
+            for hh in range(nf):
+                for name, dst in (("full_k", fk), ("full_v", fv)):
+                    _C.check(self.lib.duo_dequant_int4(t[name][b, hh].data_ptr(), t[name + "_scale"][b, hh].data_ptr(),
+                                                       t[name + "_zero"][b, hh].data_ptr(), n_rows,
+                                                       dst[b, hh].data_ptr(), stream))
+                    n += 1
+            for hh in range(ns):
+                for name, dst in (("ring_k", rk), ("ring_v", rv)):
+                    for src0, dst0, rows in ((0, 0, W), (so, W, S)):
+                        _C.check(self.lib.duo_dequant_int4(
+                            t[name][b, hh, src0:].data_ptr(), t[name + "_scale"][b, hh, src0:].data_ptr(),
+                            t[name + "_zero"][b, hh, src0:].data_ptr(), rows, dst[b, hh, dst0:].data_ptr(), stream))
+                        n += 1
+        self.launch_count += n
+        return sc["handles"][nf]
+
     def state(self, l) -> _C.CacheState:
         ds = self.dev_state.data_ptr() if self.dev_state is not None else None
         return _C.CacheState(self.kv_seq_len_list[l], self.total_list[l], self.lo_list[l], ds)
@@ -339,6 +401,9 @@ class DuoKVCache:
             _C.check(lib.duo_rope_append(ah, C.byref(ast), qkv.data_ptr(), qkv.stride(1), cp, sp,
                                          rope_mode | _C.ROPE_SKIP_Q, S, stream))
             self.launch_count += 1
+        elif (self.kv_format == "int4" and S >= 128 and self.W <= 2048 and not force_mma
+              and os.environ.get("DUO_INT4_PREFILL_SCRATCH") == "1"):
+            ah, ast = self._dequant_scratch(l, S), _C.CacheState(st.full_len, st.total, st.lo, None)
         fn = lib.duo_attention_mma if force_mma else lib.duo_attention
         if self.profile_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

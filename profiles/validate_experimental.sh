@@ -4,6 +4,7 @@
 # Every step runs under its own `timeout`; results land in gpurun_out/exp_*.{log,json}.
 #   DUO_INT4_SWAPAB=1   INT4 decode kernel with keys as the MMA M dimension (attn_int4.cu: duo_attn_int4_dec8_kernel)
 #   DUO_WIDE_MERGE=1    split-KV last-CTA merge with 16 loads in flight (duo_common.cuh: split_merge_rows4)
+#   DUO_INT4_PREFILL_SCRATCH=1  INT4 chunks >= 128 tokens: dequantise to an fp16 scratch + tcgen05 kernel (kv_cache.py)
 # (DUO_FUSED_ALLREDUCE=1 needs 2 GPUs: tests/multi_gpu/fused_allreduce_check.py, then tests/multi_gpu/tp_check.py)
 set -u
 cd "$(dirname "$0")/.."
@@ -15,22 +16,27 @@ DUO_EXPERIMENTAL=1 DUO_INT4_SWAPAB=1 run python -m pytest tests/test_gpu_int4_at
   > gpurun_out/exp_int4_swapab_tests.log 2>&1
 DUO_WIDE_MERGE=1 run python -m pytest tests/test_gpu_attention.py tests/test_gpu_model.py tests/test_gpu_int4_attention.py -x -q \
   > gpurun_out/exp_wide_merge_tests.log 2>&1
-tail -3 gpurun_out/exp_int4_swapab_tests.log gpurun_out/exp_wide_merge_tests.log
+DUO_EXPERIMENTAL=1 DUO_INT4_PREFILL_SCRATCH=1 run python -m pytest tests/test_gpu_int4_attention.py tests/test_gpu_experimental.py -x -q \
+  > gpurun_out/exp_int4_scratch_tests.log 2>&1
+tail -3 gpurun_out/exp_int4_swapab_tests.log gpurun_out/exp_wide_merge_tests.log gpurun_out/exp_int4_scratch_tests.log
 
 # 2. A/B timing: default bench line (bf16 decode @1M) with and without the wide merge
 run python bench.py --steps 8 --warmup 3 > gpurun_out/exp_bf16_base.json 2> gpurun_out/exp_bf16_base.err
 DUO_WIDE_MERGE=1 run python bench.py --steps 8 --warmup 3 > gpurun_out/exp_bf16_wide.json 2> gpurun_out/exp_bf16_wide.err
 
 # 3. A/B timing: INT4 decode @1M, current kernel vs swapped-operand kernel (both with the wide merge off, then on)
-run python bench.py --kv-format int4 --steps 8 --warmup 3 > gpurun_out/exp_int4_base.json 2> gpurun_out/exp_int4_base.err
-DUO_INT4_SWAPAB=1 run python bench.py --kv-format int4 --steps 8 --warmup 3 > gpurun_out/exp_int4_swapab.json 2> gpurun_out/exp_int4_swapab.err
+run python bench.py --kv-format int4 --no-prefill --steps 8 --warmup 3 > gpurun_out/exp_int4_base.json 2> gpurun_out/exp_int4_base.err
+DUO_INT4_SWAPAB=1 run python bench.py --kv-format int4 --no-prefill --steps 8 --warmup 3 > gpurun_out/exp_int4_swapab.json 2> gpurun_out/exp_int4_swapab.err
+# 4. INT4 prefill @128K through the scratch + tcgen05 path (the default INT4 chunk kernel is mma.sync: much slower; skip it)
+DUO_INT4_SWAPAB=1 DUO_INT4_PREFILL_SCRATCH=1 run python bench.py --kv-format int4 --prefill-reps 1 --steps 4 --warmup 3 \
+  > gpurun_out/exp_int4_scratch_prefill.json 2> gpurun_out/exp_int4_scratch_prefill.err
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/exp_*.json")):
     try:
         d = json.loads([l for l in open(f) if l.startswith("{")][-1])
         print(f, "value", round(d["value"], 2), d["unit"], "attn_ms", round(d["roofline"]["attn_ms_per_step"], 3),
-              "frac", round(d["roofline"]["frac"], 3))
+              "frac", round(d["roofline"]["frac"], 3), "prefill", (d.get("prefill") or {}).get("value"))
     except Exception as e:
         print(f, "unreadable:", e)
 PY

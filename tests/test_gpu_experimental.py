@@ -63,3 +63,13 @@ def test_int4_cuda_graph_decode_matches_eager():
                 ca.evict_last(1)
                 cb.evict_last(1)
                 graph.resync()
+
+
+def test_int4_large_chunks_batch2():
+    """Chunks of >= 128 tokens after the first call: the INT4 mma kernel by default, the dequantise-to-scratch +
+    tcgen05 path under DUO_INT4_PREFILL_SCRATCH=1 — both must match the oracle's dequantise-everything attention."""
+    from test_gpu_int4_attention import run
+
+    run(8, 2, 1, 16, 48, [300, 130, 1, 256, 1, 2, 128, 1], seed=19, B=2, stage_cap=300)
+    run(8, 2, 0, 16, 48, [200, 129, 1, 140], seed=20, stage_cap=200)   # no retrieval head in the layer
+    run(8, 2, 2, 16, 48, [200, 129, 1, 140], seed=21, stage_cap=200)   # no streaming head in the layer
