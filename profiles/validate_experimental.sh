@@ -30,6 +30,12 @@ DUO_INT4_SWAPAB=1 run python bench.py --kv-format int4 --no-prefill --steps 8 --
 # 4. INT4 prefill @128K through the scratch + tcgen05 path (the default INT4 chunk kernel is mma.sync: much slower; skip it)
 DUO_INT4_SWAPAB=1 DUO_INT4_PREFILL_SCRATCH=1 run python bench.py --kv-format int4 --prefill-reps 1 --steps 4 --warmup 3 \
   > gpurun_out/exp_int4_scratch_prefill.json 2> gpurun_out/exp_int4_scratch_prefill.err
+# 5. reference-protocol harness (eval/efficiency/benchmark_static.py), Llama-3-8B-1048k arch, 100K context
+run python eval/efficiency/benchmark_static.py --random_init llama3-8b-1048k --sparsity 0.5 --max_length 100000 \
+  --prefilling_chunk_size 32000 --ctx_steps 2 --gen_steps 50 --cuda_graph --output_dir gpurun_out/exp_harness \
+  --attn_load_dir attn_patterns/Llama-3-8B-Instruct-Gradient-1048k/lr=0.02-reg=0.05-ctx=1000_32000-multi_passkey10 \
+  > gpurun_out/exp_harness.log 2>&1
+cat gpurun_out/exp_harness/benchmark_result.txt
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/exp_*.json")):
