@@ -1255,6 +1255,9 @@ static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const v
   if (!attr_set) {
     DUO_CUDA_TRY(cudaFuncSetAttribute(duo_attn_int4_dec8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       D8_SMEM_BYTES));
+    // four CTAs of 51 KB per SM: ask for the full shared-memory carve-out
+    DUO_CUDA_TRY(cudaFuncSetAttribute(duo_attn_int4_dec8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   duo_attn_int4_dec8_kernel<<<dim3(grid_x, d.batch), I4_THREADS, D8_SMEM_BYTES, stream>>>(p);
