@@ -22,6 +22,7 @@ DECODE_MAX_Q = 16
 SYMBOLS = [
     "duo_layer_create", "duo_layer_destroy", "duo_workspace_bytes", "duo_rope_append", "duo_attention",
     "duo_attention_mma", "duo_state_advance", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
+    "duo_attention_partial", "duo_merge_partials",
     "duo_comm_data_bytes", "duo_comm_flag_bytes", "duo_comm_create", "duo_comm_destroy", "duo_allreduce_add_rmsnorm",
     "duo_last_error_string", "duo_version",
 ]
@@ -89,6 +90,10 @@ def load():
     lib.duo_add_rmsnorm.restype = C.c_int
     lib.duo_silu_mul.argtypes = [vp, vp, i64, i32, i32, vp]
     lib.duo_silu_mul.restype = C.c_int
+    lib.duo_attention_partial.argtypes = [vp, i64, vp, i64, vp, vp, i32, f32, vp, sz, vp]
+    lib.duo_attention_partial.restype = C.c_int
+    lib.duo_merge_partials.argtypes = [vp, vp, i32, i64, i32, i32, vp, i32, vp]
+    lib.duo_merge_partials.restype = C.c_int
     lib.duo_comm_data_bytes.argtypes = [i32, i32, i32, i32]
     lib.duo_comm_data_bytes.restype = sz
     lib.duo_comm_flag_bytes.argtypes = [i32, i32]

@@ -49,6 +49,11 @@ int launch_state_advance(long long* st, int n, int sink, int recent, cudaStream_
 int launch_dequant_int4(const void* packed, const void* scale, const void* zero, long long rows, void* out,
                         cudaStream_t stream);
 
+int launch_attn_mma_partial(const duo_layer* L, long long n_keys, const void* q, long long q_row_stride, float* out_o,
+                            float* out_lse, int q_len, float scale, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream);
+int launch_merge_partials(const float* o_parts, const float* lse_parts, int n_parts, long long tokens, int heads_total,
+                          int heads_used, void* out, int dtype, cudaStream_t stream);
 int launch_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res,
                        long long rows, int hidden, float eps, int dtype, cudaStream_t stream);
 int launch_silu_mul(const void* gate_up, void* out, long long rows, int inter, int dtype, cudaStream_t stream);
@@ -283,6 +288,39 @@ int duo_quant_int4(const void* in, int64_t in_row_stride, int64_t rows, void* pa
     return DUO_EINVAL;
   }
   return launch_quant_int4(in, in_row_stride, rows, packed, scale, zero, (cudaStream_t)stream);
+}
+
+int duo_attention_partial(const duo_layer* layer, int64_t n_keys, const void* q, int64_t q_row_stride, float* out_o,
+                          float* out_lse, int32_t q_len, float scale, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  if (!layer || !q || !out_o || !out_lse || n_keys < 0 || q_len < 1) {
+    set_error("duo_attention_partial: bad argument");
+    return DUO_EINVAL;
+  }
+  if (layer->d.kv_format != DUO_KV_SAME || layer->d.group * q_len > 16) {
+    set_error("duo_attention_partial: 16-bit caches and group * q_len <= 16 only (got group %d, q_len %d)",
+              layer->d.group, q_len);
+    return DUO_EINVAL;
+  }
+  if (layer->d.n_full > 0 && n_keys > layer->d.full_cap) {
+    set_error("duo_attention_partial: n_keys %lld exceeds the cache capacity %lld", (long long)n_keys,
+              (long long)layer->d.full_cap);
+    return DUO_EOVERFLOW;
+  }
+  return launch_attn_mma_partial(layer, n_keys, q, q_row_stride, out_o, out_lse, q_len, scale, workspace,
+                                 workspace_bytes, (cudaStream_t)stream);
+}
+
+int duo_merge_partials(const float* o_parts, const float* lse_parts, int32_t n_parts, int64_t tokens,
+                       int32_t heads_total, int32_t heads_used, void* out, int32_t dtype, void* stream) {
+  if (n_parts < 1 || tokens < 0 || heads_total < 1 || heads_used < 0 || heads_used > heads_total ||
+      (tokens > 0 && heads_used > 0 && (!o_parts || !lse_parts || !out)) ||
+      (dtype != DUO_DT_BF16 && dtype != DUO_DT_FP16)) {
+    set_error("duo_merge_partials: bad argument");
+    return DUO_EINVAL;
+  }
+  return launch_merge_partials(o_parts, lse_parts, n_parts, tokens, heads_total, heads_used, out, dtype,
+                               (cudaStream_t)stream);
 }
 
 int duo_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res, int64_t rows,

@@ -17,6 +17,8 @@
 //                           (decode: rows = group * q_len <= 16)
 //            KEY_WARPS=1 -> 64 packed rows per CTA, each warp owns 16 rows (small chunks and the
 //                           generic fallback for ragged prefill shapes)
+#include <type_traits>
+
 #include "duo_common.cuh"
 
 namespace duo {
@@ -46,6 +48,11 @@ struct AttnParams {
   float* ws_ml;          // [batch][n_full][n_rb][splits][ROWS][2]
   int* counters;         // [batch][n_full][n_rb]
   int wide_merge;        // experimental: split_merge_rows4 in the last-CTA merge
+  // partial mode (duo_attention_partial): fp32 normalised O + log2-domain log-sum-exp per (token, q head) instead of
+  // `out`; every query row sees all `full_len` keys (no causal offset); only retrieval heads are launched
+  float* part_o;
+  float* part_lse;
+  int no_causal;
 };
 
 template <typename T, int KEY_WARPS>
@@ -110,6 +117,10 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
   if (is_full) {
     base = p.full_len;
     long long nkeys = p.full_len + tok_max + 1;
+    if (p.no_causal) {
+      base = 1LL << 60;
+      nkeys = p.full_len;
+    }
     a0 = (long long)split * p.keys_per_split;
     a1 = min(nkeys, a0 + (long long)p.keys_per_split);
     if (a1 < a0) a1 = a0;
@@ -380,8 +391,18 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     const int R = row0 + r;
     const int tok = R / p.group;
     const int hq = kvh * p.group + R % p.group;
+    if (p.part_o) {
+      float* dst = p.part_o + (((long long)b * p.q_len + tok) * p.n_q_heads + hq) * kHeadDim + d;
+      *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+      return;
+    }
     T* dst = outb + ((long long)tok * p.n_q_heads + hq) * kHeadDim + d;
     *reinterpret_cast<uint32_t*>(dst) = Op::pack(v0, v1);
+  };
+  auto store_row_lse = [&](int r, float m_log2, float l) {  // partial mode only
+    const int R = row0 + r;
+    p.part_lse[((long long)b * p.q_len + R / p.group) * p.n_q_heads + kvh * p.group + R % p.group] =
+        l > 0.f ? m_log2 + log2f(l) : -INFINITY;
   };
 
   const int nsplit = is_full ? p.splits_full : 1;
@@ -391,6 +412,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
       const float l = sm_ml[r * 2 + 1];
       const float inv = l > 0.f ? 1.f / l : 0.f;
       store_row_elem(r, d, sm_o[r * 128 + d] * inv, sm_o[r * 128 + d + 1] * inv);
+      if (p.part_lse && d == 0) store_row_lse(r, sm_ml[r * 2], l);
     }
     return;
   }
@@ -493,6 +515,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     }
     const float inv = ll > 0.f ? 1.f / ll : 0.f;
     store_row_elem(rg + rr, d, a0f * inv, a1f * inv);
+    if (p.part_lse && d == 0) store_row_lse(rg + rr, mm, ll);
   }
   __syncthreads();
   }
@@ -519,7 +542,7 @@ size_t mma_workspace_bytes(int batch, int n_kv, int group, int max_q_len) {
 template <typename T, int KEY_WARPS>
 static int launch_variant(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride,
                           void* out, int q_len, float scale, void* workspace, size_t workspace_bytes,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, float* part_o = nullptr, float* part_lse = nullptr) {
   const duo_layer_desc& d = L->d;
   constexpr int ROWS = 16 * (4 / KEY_WARPS);
   AttnParams p{};
@@ -560,12 +583,16 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
     }
     sm_count = cached_sms;
   }
-  const long long nkeys = st->full_len + q_len;
+  const bool partial = part_o != nullptr;
+  p.part_o = part_o;
+  p.part_lse = part_lse;
+  p.no_causal = partial ? 1 : 0;
+  const long long nkeys = partial ? st->full_len : st->full_len + q_len;
   int splits = 1;
   if (d.n_full > 0) {
     const int budget = 2 * sm_count;
     const int base_ctas = d.batch * d.n_full * p.n_rb;
-    const int stream_ctas = d.batch * d.n_stream * p.n_rb;
+    const int stream_ctas = partial ? 0 : d.batch * d.n_stream * p.n_rb;
     int want = (budget - stream_ctas > 0 ? budget - stream_ctas : 1) / base_ctas;
     if (want < 1) want = 1;
     const long long max_by_len = (nkeys + 4 * TILE - 1) / (4 * TILE);  // >= 256 keys per split
@@ -598,7 +625,7 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
   p.wide_merge = wide_merge_enabled() ? 1 : 0;
 
-  const int grid_x = d.n_full * p.n_rb * splits + d.n_stream * p.n_rb;
+  const int grid_x = d.n_full * p.n_rb * splits + (partial ? 0 : d.n_stream * p.n_rb);
   if (grid_x == 0) return DUO_OK;
   auto kern = duo_attn_mma_kernel<T, KEY_WARPS>;
   static bool attr_set = false;
@@ -629,6 +656,65 @@ int launch_attn_mma(const duo_layer* L, const duo_cache_state* st, const void* q
       return launch_variant<__half, 4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
     return launch_variant<__half, 1>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
   }
+}
+
+// out[tok][h][:] = sum_p w_p o_p / sum_p w_p, w_p = 2^(lse_p - max_p lse_p): the cross-slice step of the online softmax
+// (same algebra as the last-CTA split-KV merge, one level up).  Only heads h < heads_used are touched.
+template <typename T>
+__global__ void __launch_bounds__(128) merge_partials_kernel(const float* __restrict__ o_parts,
+                                                             const float* __restrict__ lse_parts, int n_parts,
+                                                             long long tokens, int heads_total, int heads_used,
+                                                             T* __restrict__ out) {
+  const long long tok = blockIdx.x / heads_used;
+  const int h = (int)(blockIdx.x % heads_used);
+  const long long row = tok * heads_total + h;
+  const long long part_rows = tokens * heads_total;
+  float mx = -INFINITY;
+  for (int q = 0; q < n_parts; ++q) mx = fmaxf(mx, lse_parts[q * part_rows + row]);
+  float acc = 0.f, wsum = 0.f;
+  for (int q = 0; q < n_parts; ++q) {
+    const float l = lse_parts[q * part_rows + row];
+    if (l == -INFINITY) continue;
+    const float w = fast_exp2(l - mx);
+    acc += w * o_parts[(q * part_rows + row) * kHeadDim + threadIdx.x];
+    wsum += w;
+  }
+  const float v = wsum > 0.f ? acc / wsum : 0.f;
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value)
+    out[row * kHeadDim + threadIdx.x] = __float2bfloat16_rn(v);
+  else
+    out[row * kHeadDim + threadIdx.x] = __float2half_rn(v);
+}
+
+int launch_merge_partials(const float* o_parts, const float* lse_parts, int n_parts, long long tokens, int heads_total,
+                          int heads_used, void* out, int dtype, cudaStream_t stream) {
+  if (tokens == 0 || heads_used == 0) return DUO_OK;
+  const unsigned grid = (unsigned)(tokens * heads_used);
+  if (dtype == DUO_DT_BF16)
+    merge_partials_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(o_parts, lse_parts, n_parts, tokens, heads_total,
+                                                                   heads_used, (__nv_bfloat16*)out);
+  else
+    merge_partials_kernel<__half><<<grid, 128, 0, stream>>>(o_parts, lse_parts, n_parts, tokens, heads_total,
+                                                            heads_used, (__half*)out);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+// Partial attention over the first n_keys rows of every retrieval head (building block of the sequence-sharded
+// decode): decode-sized q only.
+int launch_attn_mma_partial(const duo_layer* L, long long n_keys, const void* q, long long q_row_stride, float* out_o,
+                            float* out_lse, int q_len, float scale, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream) {
+  duo_cache_state st{};
+  st.full_len = n_keys;
+  st.total = 0;
+  st.lo = L->d.sink;
+  st.device_state = nullptr;
+  if (L->d.dtype == DUO_DT_BF16)
+    return launch_variant<__nv_bfloat16, 4>(L, &st, q, q_row_stride, nullptr, q_len, scale, workspace, workspace_bytes,
+                                            stream, out_o, out_lse);
+  return launch_variant<__half, 4>(L, &st, q, q_row_stride, nullptr, q_len, scale, workspace, workspace_bytes, stream,
+                                   out_o, out_lse);
 }
 
 }  // namespace duo

@@ -205,6 +205,26 @@ DUO_API int duo_add_rmsnorm(const void* x, const void* residual, const void* wei
 DUO_API int duo_silu_mul(const void* gate_up, void* out, int64_t rows, int32_t inter, int32_t dtype, void* stream);
 
 /*
+ * EXPERIMENTAL building blocks of the sequence-sharded decode: a retrieval head's
+ * cache is split by position over several layers / ranks; each slice is attended separately and the slices are
+ * combined with the online-softmax merge (what flash_attn_func computes over the whole cache in one call,
+ * duo_attn/patch/llama.py:393-399, is recovered exactly up to fp32 rounding).
+ *   duo_attention_partial : every query row (q as for duo_attention, already rotated, group * q_len <= 16) attends rows
+ *       [0, n_keys) of EVERY retrieval head of `layer` (no causal offset, streaming heads are not computed);
+ *       out_o  : fp32 [batch][q_len][n_q_heads][128]  normalised output of the slice (retrieval-head rows only)
+ *       out_lse: fp32 [batch][q_len][n_q_heads]       log2-domain log-sum-exp: max*scale*log2(e) + log2(sum); -inf
+ *                                                      for an empty slice
+ *   duo_merge_partials    : out[tok][h][:] = sum_p 2^(lse_p - max) o_p / sum_p 2^(lse_p - max) for h < heads_used;
+ *       o_parts fp32 [n_parts][tokens][heads_total][128], lse_parts fp32 [n_parts][tokens][heads_total],
+ *       out: activation dtype [tokens][heads_total][128] (rows of heads >= heads_used are left untouched).
+ */
+DUO_API int duo_attention_partial(const duo_layer* layer, int64_t n_keys, const void* q, int64_t q_row_stride,
+                                  float* out_o, float* out_lse, int32_t q_len, float scale, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+DUO_API int duo_merge_partials(const float* o_parts, const float* lse_parts, int32_t n_parts, int64_t tokens,
+                               int32_t heads_total, int32_t heads_used, void* out, int32_t dtype, void* stream);
+
+/*
  * EXPERIMENTAL (head-parallel TP): the per-layer exchange step of the reference's
  * tensor-parallel sharding (duo_attn/utils.py:174-176, "sum" of the row-parallel o_proj / down_proj partials) as a
  * one-shot all-reduce over NVLink peer memory, fused with the residual add + RMSNorm that consumes it:
