@@ -429,7 +429,8 @@ def main():
         attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events) / args.steps
         n_attn = len(cache.profile_events) // args.steps
         cache.profile_events = None
-        if not args.no_graph and args.kv_format == "bf16":  # INT4 caches are driven eagerly (graph.py)
+        # INT4 caches are driven eagerly (graph.py) unless the experimental switch allows capturing them
+        if not args.no_graph and (args.kv_format == "bf16" or os.environ.get("DUO_EXPERIMENTAL") == "1"):
             from duo_attention_b200.graph import DuoDecodeGraph
 
             graph = DuoDecodeGraph(model, cache)

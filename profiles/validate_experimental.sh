@@ -27,6 +27,8 @@ DUO_WIDE_MERGE=1 run python bench.py --steps 8 --warmup 3 > gpurun_out/exp_bf16_
 # 3. A/B timing: INT4 decode @1M, current kernel vs swapped-operand kernel (both with the wide merge off, then on)
 run python bench.py --kv-format int4 --no-prefill --steps 8 --warmup 3 > gpurun_out/exp_int4_base.json 2> gpurun_out/exp_int4_base.err
 DUO_INT4_SWAPAB=1 run python bench.py --kv-format int4 --no-prefill --steps 8 --warmup 3 > gpurun_out/exp_int4_swapab.json 2> gpurun_out/exp_int4_swapab.err
+DUO_EXPERIMENTAL=1 DUO_INT4_SWAPAB=1 DUO_WIDE_MERGE=1 run python bench.py --kv-format int4 --no-prefill --steps 8 --warmup 3 \
+  > gpurun_out/exp_int4_swapab_graph.json 2> gpurun_out/exp_int4_swapab_graph.err   # + CUDA-graph decode driver
 # 4. INT4 prefill @128K through the scratch + tcgen05 path (the default INT4 chunk kernel is mma.sync: much slower; skip it)
 DUO_INT4_SWAPAB=1 DUO_INT4_PREFILL_SCRATCH=1 run python bench.py --kv-format int4 --prefill-reps 1 --steps 4 --warmup 3 \
   > gpurun_out/exp_int4_scratch_prefill.json 2> gpurun_out/exp_int4_scratch_prefill.err
