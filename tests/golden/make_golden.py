@@ -18,6 +18,10 @@ reordered`` (llama.py:146-306), ``..._static`` (:309-434), ``DuoAttentionStaticK
 (static_kv_cache.py:18-315), ``reorder_linear_weights`` / ``reorder_full_attn_heads``
 (patch/utils.py:6-45), ``load_attn_pattern`` / ``sparsify_attention_heads`` (duo_attn/utils.py:326-373).
 
+INT4 (``make_int4_fixtures``): ``DuoAttentionStaticINT4KVCache`` (demo/int4_kv.py:115-492) and ``LlamaAttention.forward``
+(demo/w8a8kv4_llama.py:174-287) also run unmodified, with the JIT-compiled quantisation module replaced by the NumPy
+restatement of demo/quantize_int4.cu and the absent QServe packages stubbed.
+
 Fixture inputs are regenerated from seeds by ``tests/golden_cases.py`` (shared with the tests); each
 fixture stores an fp64 checksum of its inputs so RNG drift is detected rather than silently accepted.
 """
@@ -80,6 +84,96 @@ def import_reference():
         print("duo_attn.utils import failed:", repr(e))
         ref_utils = None
     return ref_llama, ref_mistral, ref_putils, ref_utils
+
+
+def make_int4_fixtures(O, GC):
+    """Run the reference's INT4 cache class (demo/int4_kv.py:115-492, unmodified) and its attention forward
+    (demo/w8a8kv4_llama.py:174-287, unmodified, called unbound on a stand-in ``self``) on the CPU.
+
+    Swapped, because they are CUDA-only / absent: ``torch.utils.cpp_extension.load`` returns a module whose two
+    entry points are the NumPy restatement of demo/quantize_int4.cu (oracle/int4_oracle.py; pinned to the
+    reference's compiled kernels on the GPU box by tests/test_gpu_kv_ops.py); ``flash_attn_func`` -> contract
+    restatement; ``apply_rope_inplace`` -> identity (inputs are post-RoPE); QServe packages (qserve,
+    qserve_backend) -> empty stubs, the W8A8 projections around the attention are no-ops on pre-filled buffers."""
+    import torch.utils.cpp_extension as cpp
+
+    from oracle import int4_oracle as Q
+
+    class _K:
+        @staticmethod
+        def quantize_int4_with_zero_point_per_group(tensor, q_packed, scale, zero_point, group_size):
+            assert group_size == 128
+            p, s, z = Q.quantize_int4(tensor.detach().numpy())  # honours strides like quantize_int4.cu:163-165
+            q_packed.copy_(torch.from_numpy(p))
+            scale.copy_(torch.from_numpy(s))
+            zero_point.copy_(torch.from_numpy(z))
+
+        @staticmethod
+        def dequantize_int4_with_zero_point_per_group(q_packed, scale, zero_point, group_size, buffer, N):
+            assert q_packed.is_contiguous() and scale.is_contiguous() and zero_point.is_contiguous()  # raw data_ptr use
+            out = Q.dequantize_int4(q_packed.numpy().reshape(N, 64), scale.numpy().reshape(N, 1),
+                                    zero_point.numpy().reshape(N, 1))
+            buffer[: N * group_size].copy_(torch.from_numpy(out).reshape(-1))
+
+    real_load = cpp.load
+    cpp.load = lambda *a, **k: _K
+    class _Any(types.ModuleType):
+        def __getattr__(self, item):
+            if item.startswith("__"):
+                raise AttributeError(item)
+            return lambda *a, **k: None
+
+    for name in ("qserve_backend", "qserve_backend.fused_attention", "qserve_backend.fused_kernels", "qserve",
+                 "qserve.utils", "qserve.utils.constants", "qserve.modeling", "qserve.modeling.layers",
+                 "qserve.modeling.layers.activation", "qserve.modeling.layers.layernorm",
+                 "qserve.modeling.layers.quantized_linear", "qserve.modeling.layers.sampler", "qserve.sampling_params",
+                 "qserve.utils.input_metadata", "qserve.utils.quant_config", "qserve.utils.weight_utils"):
+        if name not in sys.modules:
+            m = _Any(name)
+            m.__path__ = []
+            sys.modules[name] = m
+            if "." in name:  # `import a.b.c` resolves a.b through attribute access on the parent module
+                parent, _, leaf = name.rpartition(".")
+                setattr(sys.modules[parent], leaf, m)
+    try:
+        import demo.int4_kv as ref_kv
+        import demo.w8a8kv4_llama as ref_w8
+    finally:
+        cpp.load = real_load
+    assert ref_kv.__file__.startswith(REF) and ref_w8.__file__.startswith(REF)
+    ref_w8.flash_attn_func = O.flash_attn_contract
+    ref_w8.apply_rope_inplace = lambda q, k, *a, **kw: (q, k)
+
+    for case in GC.INT4_CASES:
+        chunks = GC.make_int4_inputs(case)
+        Hq, Hkv = case["Hq"], case["Hkv"]
+        gate = [1.0] * case["n_full"] + [0.0] * (Hkv - case["n_full"])  # already "reordered": retrieval heads first
+        holder = torch.nn.Linear(1, 1).to(torch.float16)
+        model = types.SimpleNamespace(
+            parameters=lambda: holder.parameters(),
+            config=types.SimpleNamespace(num_hidden_layers=1, num_attention_heads=Hq, num_key_value_heads=Hkv,
+                                         hidden_size=Hq * GC.D))
+        cache = ref_kv.DuoAttentionStaticINT4KVCache(model, [gate], 1, case["max_size"], case["sink"], case["recent"],
+                                                     case["prefill_chunk"])
+        captured = {}
+        me = types.SimpleNamespace(
+            qkv_proj=lambda *a: None, o_proj=lambda *a: None, q_size=Hq * GC.D, kv_size=Hkv * GC.D, num_heads=Hq,
+            num_kv_heads=Hkv, head_dim=GC.D, rope_theta=10000.0, layer_idx=0, hidden_size=Hq * GC.D,
+            invoke_quant=lambda buf, attn: captured.__setitem__("out", attn.clone()))
+        outs, lens = [], []
+        for q, k, v in chunks:
+            n = q.shape[1]
+            buf = types.SimpleNamespace(
+                quantized_hidden_states_buffer=None, quantized_scale_buffer=None, out_down_proj_act_buffer=None,
+                qkv_proj_act_buffer=torch.cat([q.reshape(n, -1), k.reshape(n, -1), v.reshape(n, -1)], dim=-1),
+                batched_seq_len=n)
+            ref_w8.LlamaAttention.forward(me, types.SimpleNamespace(activation_buffer=buf), cache)
+            outs.append(captured["out"].view(1, n, Hq, GC.D))
+            lens.append((cache.kv_seq_len, cache.streaming_kv_seq_len))
+        np.savez_compressed(os.path.join(HERE, f"layer_{case['name']}.npz"),
+                            out=torch.cat(outs, dim=1).float().numpy(), lens=np.array(lens, dtype=np.int64),
+                            checksum=np.float64(GC.int4_checksum(chunks)))
+        print("wrote int4", case["name"], "tokens", sum(case["chunks"]), "final lens", lens[-1])
 
 
 def main():
@@ -176,6 +270,9 @@ def main():
                                 out=torch.cat(outs_m, dim=1).numpy().astype(np.float32),
                                 identical_to_llama=np.bool_(same), checksum=np.float64(GC.checksum(data)))
             print("wrote mistral twin", name, "identical to llama:", same)
+
+    # ---------------------------------------------------------------- INT4-KV fixtures
+    make_int4_fixtures(O, GC)
 
     # ---------------------------------------------------------------- reorder fixtures
     for case in GC.REORDER_CASES:

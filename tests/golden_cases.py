@@ -29,6 +29,36 @@ LAYER_CASES = [
 
 MISTRAL_CASES = ("tuple_g4_deploy", "static_g4_evict")  # also run through the reference's mistral.py twin
 
+# INT4-KV attention (demo/int4_kv.py cache class + demo/w8a8kv4_llama.py:174-287 forward); the reference's dequantise
+# wrapper assumes contiguous [:, :len] slices, i.e. batch 1 (int4_kv.py:91-112)
+INT4_CASES = [
+    dict(name="int4_g4_mix", Hq=8, Hkv=2, n_full=1, sink=4, recent=12, chunks=[20, 1, 1, 7, 1, 30, 1, 1], seed=41,
+         max_size=96, prefill_chunk=32),
+    dict(name="int4_g2_allfull", Hq=4, Hkv=2, n_full=2, sink=2, recent=3, chunks=[9, 1, 5, 1], seed=42, max_size=32,
+         prefill_chunk=16),
+    # (an all-streaming layer cannot run in the reference: its quantisation scratch is sized by the number of
+    #  RETRIEVAL heads, int4_kv.py:231-245, so chunk * n_stream must stay <= prefill_chunk * max n_full)
+    dict(name="int4_mha_1of4", Hq=4, Hkv=4, n_full=1, sink=3, recent=5, chunks=[6, 1, 1, 1, 1, 4, 1, 9, 1], seed=43,
+         max_size=32, prefill_chunk=32),
+]
+
+
+def make_int4_inputs(case):
+    """Post-RoPE fp16 q/k/v per chunk (RoPE is pinned separately; the fixture isolates cache + attention)."""
+    g = torch.Generator().manual_seed(case["seed"])
+    out = []
+    for n in case["chunks"]:
+        q = (torch.randn(1, n, case["Hq"], D, generator=g) * 0.9).to(torch.float16)
+        k = (torch.randn(1, n, case["Hkv"], D, generator=g) * 1.1).to(torch.float16)
+        v = (torch.randn(1, n, case["Hkv"], D, generator=g)).to(torch.float16)
+        out.append((q, k, v))
+    return out
+
+
+def int4_checksum(chunks):
+    return float(sum(float(t.double().abs().sum()) for c in chunks for t in c))
+
+
 REORDER_CASES = [
     dict(name="q_out_bias", seed=1, **{"in": 24, "out": 48}, bias=True, gate=[0.9, 0.1, 0.7, 0.2], repeat=12,
          channel="out"),

@@ -112,3 +112,22 @@ def test_oracle_matches_reference_mistral_twin(name):
     with torch.no_grad():
         out, _ = run_oracle_layer(case, data)
     np.testing.assert_allclose(out.numpy(), gold["out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", GC.INT4_CASES, ids=[c["name"] for c in GC.INT4_CASES])
+def test_oracle_int4_matches_reference_int4_forward(case):
+    """int4_attention_core vs the fixture produced by RUNNING the reference's INT4 cache class (demo/int4_kv.py) and
+    attention forward (demo/w8a8kv4_llama.py:174-287) on the same q/k/v (tests/golden/make_golden.py)."""
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", f"layer_{case['name']}.npz"))
+    chunks = GC.make_int4_inputs(case)
+    assert abs(GC.int4_checksum(chunks) - float(fx["checksum"])) < 1e-6 * float(fx["checksum"]), "input RNG drift"
+    past, outs = None, []
+    G = case["Hq"] // case["Hkv"]
+    for i, (q, k, v) in enumerate(chunks):
+        out, past = O.int4_attention_core(q, k, v, past, case["n_full"], G, case["sink"], case["recent"])
+        outs.append(out)
+        assert past[0].shape[2] == int(fx["lens"][i][0])                       # retrieval cache length
+        if case["n_full"] < case["Hkv"]:
+            assert past[1].shape[2] == int(fx["lens"][i][1])                   # compacted streaming cache length
+    got = torch.cat(outs, dim=1).float().numpy()
+    np.testing.assert_allclose(got, fx["out"], rtol=1e-5, atol=1e-6)
