@@ -18,6 +18,9 @@ reordered`` (llama.py:146-306), ``..._static`` (:309-434), ``DuoAttentionStaticK
 (static_kv_cache.py:18-315), ``reorder_linear_weights`` / ``reorder_full_attn_heads``
 (patch/utils.py:6-45), ``load_attn_pattern`` / ``sparsify_attention_heads`` (duo_attn/utils.py:326-373).
 
+Model level (``make_model_fixtures``): the reference's enable_* functions and patched ForCausalLM / Model / DecoderLayer
+forwards (tuple_kv_cache.py, static_kv_cache.py) run unmodified on a tiny HF model.
+
 INT4 (``make_int4_fixtures``): ``DuoAttentionStaticINT4KVCache`` (demo/int4_kv.py:115-492) and ``LlamaAttention.forward``
 (demo/w8a8kv4_llama.py:174-287) also run unmodified, with the JIT-compiled quantisation module replaced by the NumPy
 restatement of demo/quantize_int4.cu and the absent QServe packages stubbed.
@@ -84,6 +87,63 @@ def import_reference():
         print("duo_attn.utils import failed:", repr(e))
         ref_utils = None
     return ref_llama, ref_mistral, ref_putils, ref_utils
+
+
+def make_model_fixtures(O, GC, ref_llama, ref_mistral):
+    """Run the reference's PATCHED MODELS end to end on the CPU: ``enable_{llama,mistral}_duo_attention_eval`` (tuple
+    driver: tuple_kv_cache.py old_*_forward) and ``enable_*_duo_attention_static_kv_cache_eval`` (static driver:
+    static_kv_cache.py:318-552 / :571-805, ``DuoAttentionStaticKVCache``, ``enable_flashinfer_rmsnorm``) on a tiny
+    HF model, chunked prefill + decode [+ evict_last], last-token logits per call.
+
+    Compatibility shims only: the HF-4.45 attention attributes the reference forwards read (num_heads,
+    num_key_value_heads, hidden_size, rotary_emb, rope_theta) are added to transformers-5.5's modules, and
+    ``flashinfer.norm.rmsnorm`` (CUDA-only) is served by its fp32 formula inside the reference's own
+    ``flashinfer_rmsnorm_forward``."""
+    import duo_attn.patch.flashinfer_utils as ref_fi
+    from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+    from transformers.models.mistral.modeling_mistral import MistralRotaryEmbedding
+
+    def rmsnorm(x, w, eps=1e-6):
+        xf = x.float()
+        return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * w.float()).to(x.dtype)
+
+    ref_fi.flashinfer = types.SimpleNamespace(norm=types.SimpleNamespace(rmsnorm=rmsnorm))
+    for case in GC.MODEL_CASES:
+        model, ids, wsum = GC.make_tiny_model(case)
+        ref = ref_llama if case["kind"] == "llama" else ref_mistral
+        Rot = LlamaRotaryEmbedding if case["kind"] == "llama" else MistralRotaryEmbedding
+        for layer in model.model.layers:
+            a = layer.self_attn
+            a.num_heads, a.num_key_value_heads, a.hidden_size = 4, 2, 512
+            a.rotary_emb = Rot(config=model.config)
+            a.rope_theta = 10000.0
+        if not hasattr(model.config, "rope_scaling"):
+            model.config.rope_scaling = None
+        gates = np.array(case["gates"])
+        logits, lens = [], []
+        if case["path"] == "tuple":
+            getattr(ref, f"enable_{case['kind']}_duo_attention_eval")(model, gates, case["sink"], case["recent"])
+            past = None
+            for x in ids:
+                out = model(input_ids=x, past_key_values=past, use_cache=True)
+                past = out.past_key_values
+                logits.append(out.logits.float())
+                lens.append((past[0][0].shape[2], past[0][2].shape[2] if len(past[0]) > 2 else -1))
+        else:
+            getattr(ref, f"enable_{case['kind']}_duo_attention_static_kv_cache_eval")(model, gates)
+            cache = ref.DuoAttentionStaticKVCache(model, gates, 1, case["max_size"], case["sink"], case["recent"])
+            for i, x in enumerate(ids):
+                out = model(input_ids=x, past_key_values=cache, use_cache=True)
+                logits.append(out.logits.float())
+                ev = case.get("evict_after", {}).get(i, 0)
+                if ev:
+                    cache.evict_last(ev)
+                lens.append((cache.kv_seq_len, cache.streaming_kv_seq_len))
+        assert all(l.shape == (1, 1, GC.MODEL_VOCAB) for l in logits), [l.shape for l in logits]
+        np.savez_compressed(os.path.join(HERE, f"model_{case['name']}.npz"),
+                            logits=torch.cat(logits, dim=1).numpy(), lens=np.array(lens, dtype=np.int64),
+                            checksum=np.float64(wsum))
+        print("wrote model", case["name"], "calls", len(ids), "lens", lens[-1])
 
 
 def make_int4_fixtures(O, GC):
@@ -270,6 +330,9 @@ def main():
                                 out=torch.cat(outs_m, dim=1).numpy().astype(np.float32),
                                 identical_to_llama=np.bool_(same), checksum=np.float64(GC.checksum(data)))
             print("wrote mistral twin", name, "identical to llama:", same)
+
+    # ---------------------------------------------------------------- model-level driver fixtures
+    make_model_fixtures(O, GC, ref_llama, ref_mistral)
 
     # ---------------------------------------------------------------- INT4-KV fixtures
     make_int4_fixtures(O, GC)

@@ -59,6 +59,47 @@ def int4_checksum(chunks):
     return float(sum(float(t.double().abs().sum()) for c in chunks for t in c))
 
 
+# Model-level drivers (tuple_kv_cache.py / static_kv_cache.py patched ForCausalLM forwards + enable_* functions)
+MODEL_CASES = [
+    dict(name="llama_tuple", kind="llama", path="tuple", gates=[[1.0, 0.0], [0.0, 1.0]], sink=4, recent=6,
+         chunks=[20, 1, 1, 9, 1, 1], seed=51),
+    dict(name="llama_static", kind="llama", path="static", gates=[[1.0, 0.0], [0.0, 1.0]], sink=4, recent=6,
+         chunks=[20, 1, 1, 9, 1, 1], seed=51, max_size=64, evict_after={2: 1}),
+    dict(name="mistral_tuple", kind="mistral", path="tuple", gates=[[0.0, 1.0], [1.0, 1.0]], sink=2, recent=5,
+         chunks=[11, 1, 6, 1, 1], seed=52),
+    dict(name="mistral_static", kind="mistral", path="static", gates=[[0.0, 1.0], [1.0, 1.0]], sink=2, recent=5,
+         chunks=[11, 1, 6, 1, 1], seed=52, max_size=32, evict_after={3: 1}),
+]
+MODEL_VOCAB = 48
+
+
+def make_tiny_model(case):
+    """2-layer Llama/Mistral (4 q heads, 2 kv heads, head_dim 128, hidden 512 = heads * head_dim as the reference's
+    cache assumes, static_kv_cache.py:33-40) with every parameter drawn from a seeded generator (independent of HF's
+    initialisation order), plus the token ids of the schedule."""
+    if case["kind"] == "llama":
+        from transformers import LlamaConfig as Cfg, LlamaForCausalLM as M
+        extra = {}
+    else:
+        from transformers import MistralConfig as Cfg, MistralForCausalLM as M
+        extra = dict(sliding_window=None)
+    cfg = Cfg(hidden_size=512, num_attention_heads=4, num_key_value_heads=2, head_dim=128, num_hidden_layers=2,
+              intermediate_size=64, vocab_size=MODEL_VOCAB, max_position_embeddings=512, rope_theta=10000.0,
+              attn_implementation="eager", tie_word_embeddings=False, **extra)
+    model = M(cfg).eval()
+    g = torch.Generator().manual_seed(case["seed"])
+    tot = 0.0
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if prm.dim() == 1:
+                prm.copy_(1.0 + 0.1 * torch.randn(prm.shape, generator=g))
+            else:
+                prm.copy_(torch.randn(prm.shape, generator=g) * (1.5 / prm.shape[-1] ** 0.5))
+            tot += float(prm.double().abs().sum())
+    ids = [torch.randint(0, MODEL_VOCAB, (1, n), generator=g) for n in case["chunks"]]
+    return model, ids, tot
+
+
 REORDER_CASES = [
     dict(name="q_out_bias", seed=1, **{"in": 24, "out": 48}, bias=True, gate=[0.9, 0.1, 0.7, 0.2], repeat=12,
          channel="out"),

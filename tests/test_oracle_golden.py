@@ -131,3 +131,32 @@ def test_oracle_int4_matches_reference_int4_forward(case):
             assert past[1].shape[2] == int(fx["lens"][i][1])                   # compacted streaming cache length
     got = torch.cat(outs, dim=1).float().numpy()
     np.testing.assert_allclose(got, fx["out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", GC.MODEL_CASES, ids=[c["name"] for c in GC.MODEL_CASES])
+def test_oracle_model_matches_reference_patched_model(case):
+    """OracleModel vs logits produced by RUNNING the reference's patched models (tuple driver and static driver +
+    DuoAttentionStaticKVCache + flashinfer-rmsnorm patch, Llama and Mistral; tests/golden/make_golden.py).  The static
+    driver rotates with fp32 on-the-fly angles instead of HF's cos/sin tables: same logits up to fp32 rounding."""
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", f"model_{case['name']}.npz"))
+    model, ids, wsum = GC.make_tiny_model(case)
+    assert abs(wsum - float(fx["checksum"])) < 1e-9 * float(fx["checksum"]), "weight RNG drift"
+    om = O.OracleModel(model, np.array(case["gates"]), case["sink"], case["recent"])
+    past, got = None, []
+    for i, x in enumerate(ids):
+        lo, past = om(x, past)
+        got.append(lo)
+        ev = case.get("evict_after", {}).get(i, 0)
+        if ev:  # DuoAttentionStaticKVCache.evict_last (static_kv_cache.py:300-315) on the tuple layout
+            past = tuple((f[:, :, :-ev], s[:, :, :-ev]) for f, s in past)
+        if case["path"] == "static":
+            assert past[-1][0].shape[2] == int(fx["lens"][i][0])
+            n_stream = past[-1][1].shape[1]
+            if n_stream:
+                assert past[-1][1].shape[2] == int(fx["lens"][i][1])
+    got = torch.cat(got, dim=1).numpy()
+    tol = dict(rtol=1e-5, atol=1e-5) if case["path"] == "tuple" else dict(rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(got, fx["logits"], **tol)
+    # the schedule really exercised the streaming window (the cache was compacted at least once)
+    if case["path"] == "static" and past[0][1].shape[1]:
+        assert int(fx["lens"][:, 1].max()) <= case["sink"] + case["recent"] < int(fx["lens"][:, 0].max())
