@@ -355,6 +355,33 @@ def main():
         )
         print("wrote reorder", case["name"])
 
+    # ---------------------------------------------------------------- tensor-parallel sharding rules
+    if ref_utils is not None:
+        # get_mistral_config (duo_attn/utils.py:132-195) builds a tensor_parallel.Config out of third-party rule objects
+        # (package absent here): run it with recording stand-ins and keep the table it produces + the buffer rule
+        # to_device adds (:219-221).  tests/test_tp_gloo.py holds tp.shard_model to it.
+        rec = lambda kind: (lambda **kw: dict(kind=kind, **kw))
+        ref_utils.Split, ref_utils.SplitInChunks = rec("Split"), rec("SplitInChunks")
+        ref_utils.CollectiveOperation = lambda **kw: "collective"
+        import re as _re
+
+        # like tensor_parallel.Config, keys become compiled patterns (utils.py:189 indexes attr_rules with one)
+        ref_utils.Config = lambda **kw: types.SimpleNamespace(
+            **{name: {_re.compile(k): v for k, v in table.items()} for name, table in kw.items()})
+        mcfg = types.SimpleNamespace(model_type="mistral", hidden_size=4096, num_attention_heads=32,
+                                     num_key_value_heads=8)
+        c = ref_utils.get_mistral_config(mcfg, ["cuda:0", "cuda:1", "cuda:2", "cuda:3"])
+        rules = dict(
+            state_rules={k.pattern: v for k, v in c.state_rules.items()},
+            output_rules={k.pattern: {str(i): (o if isinstance(o, str) else "gather_kv") for i, o in v.items()}
+                          for k, v in c.output_rules.items()},
+            attr_rules={k.pattern: sorted(v) for k, v in c.attr_rules.items()},
+            buffer_rule={r".*full_attention_heads$": dict(kind="Split", dim=0)},  # to_device, utils.py:219-221
+        )
+        with open(os.path.join(HERE, "tp_rules.json"), "w") as f:
+            json.dump(rules, f, indent=1, sort_keys=True)
+        print("wrote tp rules", len(rules["state_rules"]))
+
     # ---------------------------------------------------------------- pattern fixtures
     if ref_utils is not None:
         res = {}
