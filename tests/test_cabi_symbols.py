@@ -89,3 +89,30 @@ def test_comm_entry_points_validate_before_touching_cuda():
     assert rc == _C.DUO_EOVERFLOW and "max_rows 16" in _C.last_error()
     assert lib.duo_allreduce_add_rmsnorm(out, None, None, None, None, None, 0, 1e-5, None) == _C.DUO_OK
     lib.duo_comm_destroy(out)
+
+
+def test_header_is_plain_c_and_links():
+    """include/duo_b200.h is usable from C99 (no torch / C++ types in the boundary) and a C program links against the
+    library and calls a host-only entry point."""
+    import shutil
+    import tempfile
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    _C = _ensure_built()
+    src = ('#include "duo_b200.h"\n#include <stdio.h>\n'
+           "int main(void) { duo_comm_desc d; duo_layer_desc l; duo_cache_state s; (void)d; (void)l; (void)s;\n"
+           '  printf("%d %zu\\n", duo_version(), duo_workspace_bytes(1, 8, 4, 16)); return 0; }\n')
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        libdir = os.path.dirname(_C.LIB_PATH)
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            c, "-o", exe, "-L", libdir, "-l:libduo_b200.so", "-Wl,-rpath," + libdir],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        ver, ws = out.stdout.split()
+        assert int(ver) >= 100 and int(ws) > 1 << 20
