@@ -28,7 +28,10 @@ pinned instead against the reference's *own code* executed in the build containe
 only ``flash_attn_func`` / ``apply_rope_inplace`` (CUDA-only third-party calls) swapped for
 the contract restatements in this file — see ``tests/golden/make_golden.py`` and the
 fixtures it writes — and, on the GPU box, ``flash_attn_contract`` is checked against the
-installed ``flash_attn_func`` itself (``tests/test_gpu_oracle_pin.py``).
+installed ``flash_attn_func`` itself (``tests/test_gpu_oracle_pin.py``).  The same script also runs
+the reference's patched Llama/Mistral MODELS (tuple and static drivers) and its INT4 cache class +
+W8A8KV4 attention forward; ``OracleModel`` and ``int4_attention_core`` are held to those outputs
+(``tests/test_oracle_golden.py``).
 """
 from __future__ import annotations
 
