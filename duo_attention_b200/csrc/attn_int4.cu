@@ -72,7 +72,28 @@ __device__ __forceinline__ uint32_t lop_hi(uint32_t w) {  // half2(1024 + 16 nib
   return (w & 0x00f000f0u) | 0x64006400u;
 }
 
-template <int KEY_WARPS>
+// (w & mask) | 0x64006400 as ONE LOP3 (the C expression compiles to two, both with immediate operands)
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t w, uint32_t mask, uint32_t magic) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "r"(mask), "r"(magic));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop1_lo(uint32_t w) { return lop3_and_or(w, 0x000f000fu, 0x64006400u); }
+__device__ __forceinline__ uint32_t lop1_hi(uint32_t w) { return lop3_and_or(w, 0x00f000f0u, 0x64006400u); }
+// FAST = true (EXPERIMENTAL, DUO_INT4_FAST=1): single-LOP3 conversion and the interior-tile loader path of the
+// swapped kernel below; FAST = false is the shipped code, unchanged.
+template <bool FAST>
+__device__ __forceinline__ uint32_t cv_lo(uint32_t w) {
+  if constexpr (FAST) return lop1_lo(w);
+  else return lop_lo(w);
+}
+template <bool FAST>
+__device__ __forceinline__ uint32_t cv_hi(uint32_t w) {
+  if constexpr (FAST) return lop1_hi(w);
+  else return lop_hi(w);
+}
+
+template <int KEY_WARPS, bool FAST = false>
 __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Params pin) {
   I4Params p = pin;
   if (pin.dstate) {  // occupancy lives in device memory (CUDA-graph replay)
@@ -173,6 +194,26 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
       const long long j0 = tile_start(i);
       const long long lim = min(tile_end(i), slots);  // rows >= lim are not read (zero-filled)
       const uint32_t sbase = smem_u32(smem + (i % I4_STAGES) * I4_STAGE_BYTES);
+      if constexpr (FAST) {
+        if (j0 + I4_TILE <= lim) {  // interior tile: one address per thread, immediate offsets, no predicates
+          const int r0 = tid >> 2, c = tid & 3;
+          const uint32_t doff = r0 * 64 + ((c ^ ((r0 >> 1) & 3)) << 4);
+          const long long off = (j0 + r0) * 64 + c * 16;
+#pragma unroll
+          for (int it = 0; it < I4_TILE * 4 / I4_THREADS; ++it) {
+            cp_async16(sbase + doff + it * 2048, gk + off + it * 2048, 16);
+            cp_async16(sbase + I4_PACK_BYTES + doff + it * 2048, gv + off + it * 2048, 16);
+          }
+          if (tid < I4_TILE / 2) {
+            constexpr int CPA = I4_TILE / 8;
+            const int arr = tid / CPA, qd = tid % CPA;
+            const __half* src = arr == 0 ? gks : arr == 1 ? gkz : arr == 2 ? gvs : gvz;
+            cp_async16(sbase + 2 * I4_PACK_BYTES + arr * (I4_TILE * 2) + qd * 16, src + j0 + qd * 8, 16);
+          }
+          cp_async_commit();
+          return;
+        }
+      }
 #pragma unroll
       for (int it = 0; it < I4_TILE * 4 / I4_THREADS; ++it) {
         const int chunk = tid + it * I4_THREADS;  // row = chunk/4, c = chunk%4
@@ -281,8 +322,8 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t x = ww[w], y = x >> 8;
-        Op::run(sc[n], qa[2 * w], lop_lo(x), lop_hi(x));
-        Op::run(sc[n], qa[2 * w + 1], lop_lo(y), lop_hi(y));
+        Op::run(sc[n], qa[2 * w], cv_lo<FAST>(x), cv_hi<FAST>(x));
+        Op::run(sc[n], qa[2 * w + 1], cv_lo<FAST>(y), cv_hi<FAST>(y));
       }
     }
     // ---- logits: s_j * (S_raw - qoff) + z_j * qsum, mask (boundary tiles only), online softmax --------
@@ -387,14 +428,14 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
         uint32_t r0, r1, r2, r3;  // (keys 0-7, blk) (keys 8-15, blk) (keys 0-7, blk+1) (keys 8-15, blk+1)
         ldsm_x4_trans(r0, r1, r2, r3, addr);
         const int nb = (2 * call) * 4;
-        Op::run(o[nb + 1], pa[k2], lop_lo(r0), lop_lo(r1));            // i = 1
-        Op::run(o[nb + 0], pa[k2], lop_hi(r0), lop_hi(r1));            // i = 0 (x16)
-        Op::run(o[nb + 3], pa[k2], lop_lo(r0 >> 8), lop_lo(r1 >> 8));  // i = 3
-        Op::run(o[nb + 2], pa[k2], lop_hi(r0 >> 8), lop_hi(r1 >> 8));  // i = 2 (x16)
-        Op::run(o[nb + 5], pa[k2], lop_lo(r2), lop_lo(r3));
-        Op::run(o[nb + 4], pa[k2], lop_hi(r2), lop_hi(r3));
-        Op::run(o[nb + 7], pa[k2], lop_lo(r2 >> 8), lop_lo(r3 >> 8));
-        Op::run(o[nb + 6], pa[k2], lop_hi(r2 >> 8), lop_hi(r3 >> 8));
+        Op::run(o[nb + 1], pa[k2], cv_lo<FAST>(r0), cv_lo<FAST>(r1));            // i = 1
+        Op::run(o[nb + 0], pa[k2], cv_hi<FAST>(r0), cv_hi<FAST>(r1));            // i = 0 (x16)
+        Op::run(o[nb + 3], pa[k2], cv_lo<FAST>(r0 >> 8), cv_lo<FAST>(r1 >> 8));  // i = 3
+        Op::run(o[nb + 2], pa[k2], cv_hi<FAST>(r0 >> 8), cv_hi<FAST>(r1 >> 8));  // i = 2 (x16)
+        Op::run(o[nb + 5], pa[k2], cv_lo<FAST>(r2), cv_lo<FAST>(r3));
+        Op::run(o[nb + 4], pa[k2], cv_hi<FAST>(r2), cv_hi<FAST>(r3));
+        Op::run(o[nb + 7], pa[k2], cv_lo<FAST>(r2 >> 8), cv_lo<FAST>(r3 >> 8));
+        Op::run(o[nb + 6], pa[k2], cv_hi<FAST>(r2 >> 8), cv_hi<FAST>(r3 >> 8));
       }
     }
   }
@@ -586,14 +627,6 @@ constexpr int D8_ROWS = 8;
 constexpr int D8_SMEM_BYTES = D8_STAGES * D8_STAGE_BYTES + 128;
 static_assert(D8_STAGES * D8_STAGE_BYTES >= (4 * D8_ROWS * 128 + D8_ROWS * 128 + 5 * D8_ROWS * 2) * 4, "merge smem");
 
-// (w & mask) | 0x64006400 as ONE LOP3 (the C expression compiles to two, both with immediate operands)
-__device__ __forceinline__ uint32_t lop3_and_or(uint32_t w, uint32_t mask, uint32_t magic) {
-  uint32_t d;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "r"(mask), "r"(magic));
-  return d;
-}
-__device__ __forceinline__ uint32_t lop1_lo(uint32_t w) { return lop3_and_or(w, 0x000f000fu, 0x64006400u); }
-__device__ __forceinline__ uint32_t lop1_hi(uint32_t w) { return lop3_and_or(w, 0x00f000f0u, 0x64006400u); }
 __device__ __forceinline__ float lds_half(uint32_t addr) {
   unsigned short h;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
@@ -1150,7 +1183,11 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
   p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
   const int grid_x = d.n_full * p.n_rb * splits + d.n_stream * p.n_rb;
   if (grid_x == 0) return DUO_OK;
-  auto kern = duo_attn_int4_kernel<KEY_WARPS>;
+  static const bool fast = [] {  // experimental variant, opt-in until validated on hardware
+    const char* e = getenv("DUO_INT4_FAST");
+    return e != nullptr && e[0] == '1';
+  }();
+  auto kern = fast ? duo_attn_int4_kernel<KEY_WARPS, true> : duo_attn_int4_kernel<KEY_WARPS, false>;
   static bool attr_set = false;
   if (!attr_set) {
     DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, I4_SMEM_BYTES));
