@@ -19,6 +19,8 @@
 //
 // Masks: retrieval heads use bottom-right causal over [cache | chunk]; streaming heads attend the
 // live sink/ring slots (validity table in smem) plus the staged chunk causally — see duo_b200.h.
+#include <cstdlib>
+
 #include "duo_common.cuh"
 
 namespace duo {
@@ -41,6 +43,7 @@ struct TcParams {
   int n_tok_items;   // token-tile items per (kv head, head item)
   int n_head_items;  // head items per kv head
   int pair_heads;    // 1: slots are two heads (G even); 0: slots are two token tiles (G odd)
+  int warp_arrive;   // EXPERIMENTAL (DUO_TC_WARP_ARRIVE=1): one p_full arrival per softmax warp instead of per thread
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -213,7 +216,7 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_init(&bars.v_full[s], 1);
       mbar_init(&bars.v_empty[s], 1);
       mbar_init(&bars.s_full[s], 1);
-      mbar_init(&bars.p_full[s], 128);
+      mbar_init(&bars.p_full[s], p.warp_arrive ? 4 : 128);
       mbar_init(&bars.o_done[s], 1);
     }
     fence_barrier_init();
@@ -391,7 +394,12 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           l_run += rs;
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&bars.p_full[slot]);
+          if (p.warp_arrive) {  // 128 arrivals on one mbarrier serialise; the path taken is warp-uniform (votes)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.p_full[slot]);
+          } else {
+            mbar_arrive(&bars.p_full[slot]);
+          }
           continue;
         }
       }
@@ -458,7 +466,12 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       l_run += rs;
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars.p_full[slot]);
+      if (p.warp_arrive) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.p_full[slot]);
+      } else {
+        mbar_arrive(&bars.p_full[slot]);
+      }
     }
 
     // ---- epilogue: O / l -> global ----------------------------------------------------------------
@@ -532,6 +545,13 @@ int launch_attn_tc(const duo_layer* L, const duo_cache_state* st, const void* q,
     }
   }
   TcParams p{};
+  {
+    static const bool wa = [] {  // opt-in until validated on hardware
+      const char* e = getenv("DUO_TC_WARP_ARRIVE");
+      return e != nullptr && e[0] == '1';
+    }();
+    p.warp_arrive = wa ? 1 : 0;
+  }
   p.out = out;
   const int n_q = (d.n_full + d.n_stream) * d.group;
   p.out_batch_stride = (long long)q_len * n_q * kHeadDim;

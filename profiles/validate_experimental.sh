@@ -4,6 +4,7 @@
 # Every step runs under its own `timeout`; results land in gpurun_out/exp_*.{log,json}.
 #   DUO_INT4_SWAPAB=1   INT4 decode kernel with keys as the MMA M dimension (attn_int4.cu: duo_attn_int4_dec8_kernel)
 #   DUO_INT4_FAST=1     shipped INT4 kernels with the single-LOP3 conversion + interior-tile loader path (template FAST)
+#   DUO_TC_WARP_ARRIVE=1  tcgen05 prefill kernel: one p_full mbarrier arrival per softmax warp instead of per thread
 #   DUO_WIDE_MERGE=1    split-KV last-CTA merge with 16 loads in flight (duo_common.cuh: split_merge_rows4)
 #   DUO_INT4_PREFILL_SCRATCH=1  INT4 chunks >= 128 tokens: dequantise to an fp16 scratch + tcgen05 kernel (kv_cache.py)
 # (DUO_FUSED_ALLREDUCE=1 needs 2 GPUs: tests/multi_gpu/fused_allreduce_check.py, then tests/multi_gpu/tp_check.py)
@@ -22,6 +23,13 @@ DUO_WIDE_MERGE=1 run python -m pytest tests/test_gpu_attention.py tests/test_gpu
 DUO_EXPERIMENTAL=1 DUO_INT4_PREFILL_SCRATCH=1 run python -m pytest tests/test_gpu_int4_attention.py tests/test_gpu_experimental.py -x -q \
   > gpurun_out/exp_int4_scratch_tests.log 2>&1
 tail -3 gpurun_out/exp_int4_swapab_tests.log gpurun_out/exp_int4_fast_tests.log gpurun_out/exp_wide_merge_tests.log gpurun_out/exp_int4_scratch_tests.log
+
+DUO_TC_WARP_ARRIVE=1 run python -m pytest tests/test_gpu_attention.py tests/test_gpu_model.py -x -q \
+  > gpurun_out/exp_tc_warp_arrive_tests.log 2>&1
+tail -3 gpurun_out/exp_tc_warp_arrive_tests.log
+run python profiles/bench_tc.py > gpurun_out/exp_tc_base.log 2>&1
+DUO_TC_WARP_ARRIVE=1 run python profiles/bench_tc.py > gpurun_out/exp_tc_warp_arrive.log 2>&1
+tail -2 gpurun_out/exp_tc_base.log gpurun_out/exp_tc_warp_arrive.log
 
 # 2. A/B timing: default bench line (bf16 decode @1M) with and without the wide merge
 run python bench.py --steps 8 --warmup 3 > gpurun_out/exp_bf16_base.json 2> gpurun_out/exp_bf16_base.err
