@@ -315,3 +315,140 @@ def test_swapab_fully_masked_rows_stay_empty():
     assert np.all(np.isfinite(O))
     ref = truth(q[:1], kp, ks, kz, vp, vs, vz, group, 0.1 / 1.4426950408889634, 10 ** 9, visible=vis[:1])
     assert np.abs(O[0] / l[0] - ref[0]).max() < 4e-3 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Cross-check of the emulated primitives: the SHIPPED kernel (duo_attn_int4_kernel<4>, hardware-validated in
+# tests/test_gpu_int4_attention.py) replayed with the same mma / ldmatrix.trans / LOP emulation must be correct too.
+# ------------------------------------------------------------------------------------------------------------------
+def emulate_shipped_warp(q, kp, ks, kz, vp, vs, vz, group, scale_log2):
+    """One warp of duo_attn_int4_kernel<4> (rows as M = 16, keys as N) over ONE 32-key tile, no mask."""
+    rows_total = q.shape[0]
+    q16 = np.zeros((16, 128), np.float16)
+    q16[:rows_total] = q
+    qa = [[[0] * 4 for _ in range(8)] for _ in LANES]
+    qsum = [[F(0)] * 2 for _ in LANES]
+    qoff = [[F(0)] * 2 for _ in LANES]
+    for lane in LANES:
+        g, t4 = lane >> 2, lane & 3
+        for hf in range(2):
+            s_all = F(0)
+            s_off = F(0)
+            for w in range(4):
+                e = q16[g + 8 * hf, 32 * t4 + 8 * w: 32 * t4 + 8 * w + 8]
+                h = (e * np.float16(0.0625)).astype(np.float16)
+                qa[lane][2 * w][hf] = pack_h2(e[1], e[5])
+                qa[lane][2 * w][hf + 2] = pack_h2(h[0], h[4])
+                qa[lane][2 * w + 1][hf] = pack_h2(e[3], e[7])
+                qa[lane][2 * w + 1][hf + 2] = pack_h2(h[2], h[6])
+                s_all += e.astype(F).sum()
+                s_off += F(1024.0) * (F(e[1]) + F(e[5]) + F(e[3]) + F(e[7]) + F(h[0]) + F(h[4]) + F(h[2]) + F(h[6]))
+            qsum[lane][hf], qoff[lane][hf] = s_all, s_off
+    for lane in LANES:  # butterfly over t4
+        pass
+    red = lambda arr, hf: [sum(arr[(lane & ~3) + k][hf] for k in range(4)) for lane in LANES]
+    for hf in range(2):
+        a, b = red(qsum, hf), red(qoff, hf)
+        for lane in LANES:
+            qsum[lane][hf], qoff[lane][hf] = a[lane], b[lane]
+    sK, sV = tile_image(kp), tile_image(vp)
+    NT = 4
+    sc = [[[F(0)] * 4 for _ in range(NT)] for _ in LANES]
+    for n in range(NT):
+        acc = [[F(0)] * 4 for _ in LANES]
+        words = []
+        for lane in LANES:
+            g, t4 = lane >> 2, lane & 3
+            key = n * 8 + g
+            a0 = key * 64 + ((t4 ^ ((key >> 1) & 3)) << 4)
+            words.append(sK[a0:a0 + 16].view(np.uint32))
+        for w in range(4):
+            for half in range(2):
+                bf = []
+                for lane in LANES:
+                    x = int(words[lane][w]) >> (8 * half)
+                    bf.append([lop_lo(x), lop_hi(x)])
+                mma_16816(acc, [qa[lane][2 * w + half] for lane in LANES], bf)
+        for lane in LANES:
+            sc[lane][n] = acc[lane]
+    tks, tkz, tvs, tvz = (a.astype(F) for a in (ks, kz, vs, vz))
+    for lane in LANES:
+        g, t4 = lane >> 2, lane & 3
+        for n in range(NT):
+            for e in range(4):
+                kc = n * 8 + 2 * t4 + (e & 1)
+                hf = e >> 1
+                ok = (g + 8 * hf) < rows_total
+                v = tks[kc] * (sc[lane][n][e] - qoff[lane][hf]) + tkz[kc] * qsum[lane][hf]
+                sc[lane][n][e] = F(v) if ok else F(-np.inf)
+    m = [[F(-np.inf)] * 2 for _ in LANES]
+    for hf in range(2):
+        for lane in LANES:
+            base = lane & ~3
+            m[lane][hf] = max(sc[base + k][n][2 * hf + e] for k in range(4) for n in range(NT) for e in range(2))
+    l = [[F(0)] * 2 for _ in LANES]
+    ps = [[F(0)] * 2 for _ in LANES]
+    pz = [[F(0)] * 2 for _ in LANES]
+    pa = [[[0] * 4 for _ in range(NT // 2)] for _ in LANES]
+    for lane in LANES:
+        t4 = lane & 3
+        for n in range(NT):
+            kc = n * 8 + 2 * t4
+            pv = []
+            for e in range(4):
+                hf = e >> 1
+                msc = F(0) if m[lane][hf] == -np.inf else F(m[lane][hf] * scale_log2)
+                pv.append(F(np.exp2(F(sc[lane][n][e] * scale_log2) - msc)))
+            for hf in range(2):
+                p0, p1 = pv[2 * hf], pv[2 * hf + 1]
+                l[lane][hf] += p0 + p1
+                pz[lane][hf] += p0 * tvz[kc] + p1 * tvz[kc + 1]
+                packed = pack_h2(p0 * tvs[kc], p1 * tvs[kc + 1])
+                ps[lane][hf] += h2(packed).sum()
+                pa[lane][n >> 1][(n & 1) * 2 + hf] = packed
+    o = [[[F(0)] * 4 for _ in range(16)] for _ in LANES]
+    for k2 in range(NT // 2):
+        for call in range(2):
+            addrs = []
+            for lane in LANES:
+                lrow, lmat = lane & 7, lane >> 3
+                key = k2 * 16 + (lmat & 1) * 8 + lrow
+                blk = 2 * call + (lmat >> 1)
+                addrs.append(key * 64 + ((blk ^ ((key >> 1) & 3)) << 4))
+            r = ldsm_x4_trans(sV, addrs)
+            nb = 2 * call * 4
+            for off, ra, rb, fn, sh in ((1, 0, 1, lop_lo, 0), (0, 0, 1, lop_hi, 0), (3, 0, 1, lop_lo, 8), (2, 0, 1, lop_hi, 8),
+                                        (5, 2, 3, lop_lo, 0), (4, 2, 3, lop_hi, 0), (7, 2, 3, lop_lo, 8), (6, 2, 3, lop_hi, 8)):
+                acc = [o[lane][nb + off] for lane in LANES]
+                mma_16816(acc, [pa[lane][k2] for lane in LANES],
+                          [[fn(r[lane][ra] >> sh), fn(r[lane][rb] >> sh)] for lane in LANES])
+    O = np.zeros((16, 128), F)
+    L = np.zeros(16, F)
+    for lane in LANES:
+        g, t4 = lane >> 2, lane & 3
+        for hf in range(2):
+            row = g + 8 * hf
+            base = lane & ~3
+            L[row] = sum(l[base + k][hf] for k in range(4))
+            pst = sum(ps[base + k][hf] for k in range(4))
+            pzt = sum(pz[base + k][hf] for k in range(4))
+            for nt in range(16):
+                blk, ii = nt >> 2, nt & 3
+                mul = F(1.0) if ii & 1 else F(0.0625)
+                for e in range(2):
+                    d = 32 * blk + 4 * (2 * t4 + e) + ii
+                    O[row, d] = (o[lane][nt][hf * 2 + e] - F(1024.0) * pst) * mul + pzt
+    return O, L
+
+
+def test_emulated_primitives_reproduce_the_shipped_kernel_algebra():
+    rows, group, n_keys = 4, 4, 32
+    q, kp, ks, kz, vp, vs, vz = _case(77, n_keys, rows, group)
+    scale = 128 ** -0.5
+    O, l = emulate_shipped_warp(q, kp, ks, kz, vp, vs, vz, group, F(scale * 1.4426950408889634))
+    ref = truth(q, kp, ks, kz, vp, vs, vz, group, scale, 10 ** 9)
+    got = O[:rows] / l[:rows, None]
+    assert np.abs(got - ref).max() < 4e-3 * max(1.0, np.abs(ref).max())
+    # and both formulations agree with each other far below the fp16-P rounding noise
+    O2, _, l2 = emulate_warp(q, kp, ks, kz, vp, vs, vz, group, F(scale * 1.4426950408889634), 10 ** 9)
+    assert np.abs(O2[:rows] / l2[:rows, None] - got).max() < 2e-3
