@@ -429,8 +429,7 @@ def main():
         attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events) / args.steps
         n_attn = len(cache.profile_events) // args.steps
         cache.profile_events = None
-        # INT4 caches are driven eagerly (graph.py) unless the experimental switch allows capturing them
-        if not args.no_graph and (args.kv_format == "bf16" or os.environ.get("DUO_EXPERIMENTAL") == "1"):
+        if not args.no_graph:
             from duo_attention_b200.graph import DuoDecodeGraph
 
             graph = DuoDecodeGraph(model, cache)
@@ -488,7 +487,7 @@ def main():
                                      "ratio of the ncu --set full capture (profiles/r1_decode.md)",
                      "achieved_note": "algorithmic bytes of the 32 attention launches of a step / sum of their "
                                       "CUDA-event durations (eager pass on the launching stream)",
-                     "kernel": ("duo_attn_int4_kernel" if args.kv_format == "int4" else "duo_attn_mma_kernel")
+                     "kernel": ("duo_attn_int4_dec8_kernel" if args.kv_format == "int4" else "duo_attn_mma_kernel")
                                + " (decode, all layers of one step)",
                      "attn_ms_per_step": attn_ms, "attn_ms_per_step_max_rank": attn_ms_max,
                      "launches_per_step": n_attn, "algorithmic_bytes_per_step": by,

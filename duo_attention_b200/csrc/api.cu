@@ -10,12 +10,17 @@
 
 namespace duo {
 
-bool wide_merge_enabled() {  // experimental split-KV merge variant, opt-in until validated on hardware
-  static const bool on = [] {
-    const char* e = getenv("DUO_WIDE_MERGE");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
+int sm_count_current_device() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& v = sms[dev & 63];
+  if (v == 0) {
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    v = n;
+  }
+  return v;
 }
 
 static thread_local char g_err[512] = "";
@@ -46,6 +51,7 @@ int launch_stream_commit(const duo_layer* L, const duo_cache_state* st, int q_le
 int launch_quant_int4(const void* in, long long in_row_stride, long long rows, void* packed, void* scale, void* zero,
                       cudaStream_t stream);
 int launch_state_advance(long long* st, int n, int sink, int recent, cudaStream_t stream);
+int launch_state_set(long long* st, long long full_len, long long total, long long lo, cudaStream_t stream);
 int launch_dequant_int4(const void* packed, const void* scale, const void* zero, long long rows, void* out,
                         cudaStream_t stream);
 
@@ -273,6 +279,14 @@ int duo_state_advance(int64_t* device_state, int32_t n, int32_t sink, int32_t re
     return DUO_EINVAL;
   }
   return launch_state_advance(reinterpret_cast<long long*>(device_state), n, sink, recent, (cudaStream_t)stream);
+}
+
+int duo_state_set(int64_t* device_state, int64_t full_len, int64_t total, int64_t lo, void* stream) {
+  if (!device_state || full_len < 0 || total < 0 || lo < 0) {
+    set_error("duo_state_set: bad argument");
+    return DUO_EINVAL;
+  }
+  return launch_state_set(reinterpret_cast<long long*>(device_state), full_len, total, lo, (cudaStream_t)stream);
 }
 
 int duo_stream_commit(const duo_layer* layer, const duo_cache_state* st, int32_t q_len, void* stream) {

@@ -65,14 +65,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ uint32_t lop_lo(uint32_t w) {  // half2(1024 + nib[bits 0-3], 1024 + nib[bits 16-19])
-  return (w & 0x000f000fu) | 0x64006400u;
-}
-__device__ __forceinline__ uint32_t lop_hi(uint32_t w) {  // half2(1024 + 16 nib[bits 4-7], 1024 + 16 nib[bits 20-23])
-  return (w & 0x00f000f0u) | 0x64006400u;
-}
-
-// (w & mask) | 0x64006400 as ONE LOP3 (the C expression compiles to two, both with immediate operands)
+// (w & mask) | 0x64006400 as ONE LOP3 (the C expression compiles to two, both with immediate operands):
+//   lop1_lo: half2(1024 + nib[bits 0-3], 1024 + nib[bits 16-19])
+//   lop1_hi: half2(1024 + 16 nib[bits 4-7], 1024 + 16 nib[bits 20-23])
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t w, uint32_t mask, uint32_t magic) {
   uint32_t d;
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "r"(mask), "r"(magic));
@@ -80,20 +75,8 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t w, uint32_t mask, uint3
 }
 __device__ __forceinline__ uint32_t lop1_lo(uint32_t w) { return lop3_and_or(w, 0x000f000fu, 0x64006400u); }
 __device__ __forceinline__ uint32_t lop1_hi(uint32_t w) { return lop3_and_or(w, 0x00f000f0u, 0x64006400u); }
-// FAST = true (EXPERIMENTAL, DUO_INT4_FAST=1): single-LOP3 conversion and the interior-tile loader path of the
-// swapped kernel below; FAST = false is the shipped code, unchanged.
-template <bool FAST>
-__device__ __forceinline__ uint32_t cv_lo(uint32_t w) {
-  if constexpr (FAST) return lop1_lo(w);
-  else return lop_lo(w);
-}
-template <bool FAST>
-__device__ __forceinline__ uint32_t cv_hi(uint32_t w) {
-  if constexpr (FAST) return lop1_hi(w);
-  else return lop_hi(w);
-}
 
-template <int KEY_WARPS, bool FAST = false>
+template <int KEY_WARPS>
 __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Params pin) {
   I4Params p = pin;
   if (pin.dstate) {  // occupancy lives in device memory (CUDA-graph replay)
@@ -194,7 +177,7 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
       const long long j0 = tile_start(i);
       const long long lim = min(tile_end(i), slots);  // rows >= lim are not read (zero-filled)
       const uint32_t sbase = smem_u32(smem + (i % I4_STAGES) * I4_STAGE_BYTES);
-      if constexpr (FAST) {
+      {
         if (j0 + I4_TILE <= lim) {  // interior tile: one address per thread, immediate offsets, no predicates
           const int r0 = tid >> 2, c = tid & 3;
           const uint32_t doff = r0 * 64 + ((c ^ ((r0 >> 1) & 3)) << 4);
@@ -322,8 +305,8 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t x = ww[w], y = x >> 8;
-        Op::run(sc[n], qa[2 * w], cv_lo<FAST>(x), cv_hi<FAST>(x));
-        Op::run(sc[n], qa[2 * w + 1], cv_lo<FAST>(y), cv_hi<FAST>(y));
+        Op::run(sc[n], qa[2 * w], lop1_lo(x), lop1_hi(x));
+        Op::run(sc[n], qa[2 * w + 1], lop1_lo(y), lop1_hi(y));
       }
     }
     // ---- logits: s_j * (S_raw - qoff) + z_j * qsum, mask (boundary tiles only), online softmax --------
@@ -428,14 +411,14 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
         uint32_t r0, r1, r2, r3;  // (keys 0-7, blk) (keys 8-15, blk) (keys 0-7, blk+1) (keys 8-15, blk+1)
         ldsm_x4_trans(r0, r1, r2, r3, addr);
         const int nb = (2 * call) * 4;
-        Op::run(o[nb + 1], pa[k2], cv_lo<FAST>(r0), cv_lo<FAST>(r1));            // i = 1
-        Op::run(o[nb + 0], pa[k2], cv_hi<FAST>(r0), cv_hi<FAST>(r1));            // i = 0 (x16)
-        Op::run(o[nb + 3], pa[k2], cv_lo<FAST>(r0 >> 8), cv_lo<FAST>(r1 >> 8));  // i = 3
-        Op::run(o[nb + 2], pa[k2], cv_hi<FAST>(r0 >> 8), cv_hi<FAST>(r1 >> 8));  // i = 2 (x16)
-        Op::run(o[nb + 5], pa[k2], cv_lo<FAST>(r2), cv_lo<FAST>(r3));
-        Op::run(o[nb + 4], pa[k2], cv_hi<FAST>(r2), cv_hi<FAST>(r3));
-        Op::run(o[nb + 7], pa[k2], cv_lo<FAST>(r2 >> 8), cv_lo<FAST>(r3 >> 8));
-        Op::run(o[nb + 6], pa[k2], cv_hi<FAST>(r2 >> 8), cv_hi<FAST>(r3 >> 8));
+        Op::run(o[nb + 1], pa[k2], lop1_lo(r0), lop1_lo(r1));            // i = 1
+        Op::run(o[nb + 0], pa[k2], lop1_hi(r0), lop1_hi(r1));            // i = 0 (x16)
+        Op::run(o[nb + 3], pa[k2], lop1_lo(r0 >> 8), lop1_lo(r1 >> 8));  // i = 3
+        Op::run(o[nb + 2], pa[k2], lop1_hi(r0 >> 8), lop1_hi(r1 >> 8));  // i = 2 (x16)
+        Op::run(o[nb + 5], pa[k2], lop1_lo(r2), lop1_lo(r3));
+        Op::run(o[nb + 4], pa[k2], lop1_hi(r2), lop1_hi(r3));
+        Op::run(o[nb + 7], pa[k2], lop1_lo(r2 >> 8), lop1_lo(r3 >> 8));
+        Op::run(o[nb + 6], pa[k2], lop1_hi(r2 >> 8), lop1_hi(r3 >> 8));
       }
     }
   }
@@ -542,40 +525,20 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
   float* cm_ml = reinterpret_cast<float*>(smem + 80 * 1024);
   for (int rg = 0; rg < rows_here; rg += 16) {
     const int rg_n = min(16, rows_here - rg);
-    for (int rr = 0; rr < rg_n; ++rr) {
-      const int r = rg + rr;
-      float mm = -INFINITY, ll = 0.f;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s0 = warp; s0 < p.splits_full; s0 += 16) {
-        float ms[4], ls[4];
-        float4 vs[4];
+    for (int rr0 = 0; rr0 < rg_n; rr0 += 4) {  // four rows per pass: 16 loads in flight (split_merge_rows4)
+      const int nr = min(4, rg_n - rr0);
+      float4 acc4[4];
+      float mm4[4], ll4[4];
+      split_merge_rows4<ROWS>(po, pml, p.splits_full, warp, lane, rg + rr0, nr, acc4, mm4, ll4);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int s2 = s0 + 4 * u;
-          const bool ok = s2 < p.splits_full;
-          const int sc2 = ok ? s2 : s0;
-          ms[u] = ok ? __ldcg(&pml[(sc2 * ROWS + r) * 2]) : -INFINITY;
-          ls[u] = __ldcg(&pml[(sc2 * ROWS + r) * 2 + 1]);
-          vs[u] = __ldcg(reinterpret_cast<const float4*>(&po[((long long)sc2 * ROWS + r) * 128 + lane * 4]));
+      for (int q = 0; q < 4; ++q) {
+        if (q < nr) {
+          *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr0 + q) * 128 + lane * 4]) = acc4[q];
+          if (lane == 0) {
+            cm_ml[(warp * 16 + rr0 + q) * 2] = mm4[q];
+            cm_ml[(warp * 16 + rr0 + q) * 2 + 1] = ll4[q];
+          }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (ms[u] == -INFINITY) continue;
-          const float mn = fmaxf(mm, ms[u]);
-          const float fo = (mm == -INFINITY) ? 0.f : fast_exp2(mm - mn);
-          const float fn = fast_exp2(ms[u] - mn);
-          acc.x = acc.x * fo + vs[u].x * fn;
-          acc.y = acc.y * fo + vs[u].y * fn;
-          acc.z = acc.z * fo + vs[u].z * fn;
-          acc.w = acc.w * fo + vs[u].w * fn;
-          ll = ll * fo + ls[u] * fn;
-          mm = mn;
-        }
-      }
-      *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr) * 128 + lane * 4]) = acc;
-      if (lane == 0) {
-        cm_ml[(warp * 16 + rr) * 2] = mm;
-        cm_ml[(warp * 16 + rr) * 2 + 1] = ll;
       }
     }
     __syncthreads();
@@ -616,8 +579,9 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
 // constant-one A fragment per 16 keys instead of unpack+add on the ALU pipe, and the running-max reduction
 // across lanes is only executed on tiles where some lane saw a logit above the running max.
 //
-// EXPERIMENTAL: selected only when the environment variable DUO_INT4_SWAPAB=1 is set (see launch_attn_int4).
-// The fragment algebra is checked lane-by-lane on the CPU in tests/test_int4_swapab_layout.py.
+// Measured on the B200 box (1M-token decode, profiles/r2_validation.md): 7.20 -> 5.11 ms of attention per step against
+// the row-major kernel.  The fragment algebra is also checked lane-by-lane on the CPU
+// (tests/test_int4_swapab_layout.py).
 // =============================================================================================
 constexpr int D8_TILE = 128;
 constexpr int D8_STAGES = 3;
@@ -1138,17 +1102,7 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
   p.rvs = (const __half*)d.ring_v_scale;
   p.rvz = (const __half*)d.ring_v_zero;
 
-  int sm_count = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    static int cached_dev = -1, cached_sms = 148;
-    if (cached_dev != dev) {
-      cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
-      cached_dev = dev;
-    }
-    sm_count = cached_sms;
-  }
+  const int sm_count = sm_count_current_device();
   const long long nkeys = st->full_len + q_len;
   int splits = 1;
   if (d.n_full > 0) {
@@ -1183,22 +1137,15 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
   p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
   const int grid_x = d.n_full * p.n_rb * splits + d.n_stream * p.n_rb;
   if (grid_x == 0) return DUO_OK;
-  static const bool fast = [] {  // experimental variant, opt-in until validated on hardware
-    const char* e = getenv("DUO_INT4_FAST");
-    return e != nullptr && e[0] == '1';
-  }();
-  auto kern = fast ? duo_attn_int4_kernel<KEY_WARPS, true> : duo_attn_int4_kernel<KEY_WARPS, false>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, I4_SMEM_BYTES));
-    attr_set = true;
-  }
+  auto kern = duo_attn_int4_kernel<KEY_WARPS>;
+  static unsigned long long attr_mask = 0;
+  if (int rc = ensure_dyn_smem(kern, I4_SMEM_BYTES, &attr_mask)) return rc;
   kern<<<dim3(grid_x, d.batch), I4_THREADS, I4_SMEM_BYTES, stream>>>(p);
   DUO_CUDA_TRY(cudaGetLastError());
   return DUO_OK;
 }
 
-// EXPERIMENTAL launch of duo_attn_int4_dec8_kernel (group * q_len <= 8): 4 CTAs / SM, 8-row split-KV workspace.
+// Launch of duo_attn_int4_dec8_kernel (group * q_len <= 8): 4 CTAs / SM, 8-row split-KV workspace.
 static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride,
                           void* out, int q_len, float scale, void* workspace, size_t workspace_bytes,
                           cudaStream_t stream) {
@@ -1242,17 +1189,7 @@ static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const v
   p.rvs = (const __half*)d.ring_v_scale;
   p.rvz = (const __half*)d.ring_v_zero;
 
-  int sm_count = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    static int cached_dev = -1, cached_sms = 148;
-    if (cached_dev != dev) {
-      cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
-      cached_dev = dev;
-    }
-    sm_count = cached_sms;
-  }
+  const int sm_count = sm_count_current_device();
   const long long nkeys = st->full_len + q_len;
   int splits = 1;
   if (d.n_full > 0) {
@@ -1288,31 +1225,16 @@ static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const v
   p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
   const int grid_x = d.n_full * splits + d.n_stream;
   if (grid_x == 0) return DUO_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DUO_CUDA_TRY(cudaFuncSetAttribute(duo_attn_int4_dec8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      D8_SMEM_BYTES));
-    // four CTAs of 51 KB per SM: ask for the full shared-memory carve-out
-    DUO_CUDA_TRY(cudaFuncSetAttribute(duo_attn_int4_dec8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;  // four CTAs of 51 KB per SM: also ask for the full smem carve-out
+  if (int rc = ensure_dyn_smem(duo_attn_int4_dec8_kernel, D8_SMEM_BYTES, &attr_mask, true)) return rc;
   duo_attn_int4_dec8_kernel<<<dim3(grid_x, d.batch), I4_THREADS, D8_SMEM_BYTES, stream>>>(p);
   DUO_CUDA_TRY(cudaGetLastError());
   return DUO_OK;
 }
 
-static bool swapab_enabled() {  // experimental kernel: opt-in until it has been validated on hardware
-  static const bool on = [] {
-    const char* e = getenv("DUO_INT4_SWAPAB");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
 int launch_attn_int4(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
                      int q_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (L->d.group * q_len <= D8_ROWS && swapab_enabled())
+  if (L->d.group * q_len <= D8_ROWS)
     return launch_i4_dec8(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);
   if (L->d.group * q_len <= 16)
     return launch_i4<4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream);

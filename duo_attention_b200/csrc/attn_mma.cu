@@ -47,7 +47,6 @@ struct AttnParams {
   float* ws_o;           // [batch][n_full][n_rb][splits][ROWS][128]
   float* ws_ml;          // [batch][n_full][n_rb][splits][ROWS][2]
   int* counters;         // [batch][n_full][n_rb]
-  int wide_merge;        // experimental: split_merge_rows4 in the last-CTA merge
   // partial mode (duo_attention_partial): fp32 normalised O + log2-domain log-sum-exp per (token, q head) instead of
   // `out`; every query row sees all `full_len` keys (no causal offset); only retrieval heads are launched
   float* part_o;
@@ -435,66 +434,30 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  // Parallel merge: warp w takes splits w, w+4, ... (lane = 4 output dims), merges them online with 4
-  // independent loads in flight per row, then the 4 warps' partials are merged through shared memory.
+  // Parallel merge: warp w takes splits w, w+4, ... (lane = 4 output dims) and merges them online, then the 4 warps'
+  // partials are merged through shared memory.
   const float* po = p.ws_o + item * p.splits_full * (long long)(ROWS * 128);
   const float* pml = p.ws_ml + item * p.splits_full * (long long)(ROWS * 2);
   float* cm_o = reinterpret_cast<float*>(smem);               // [4 warps][16][128]  (rows in groups of 16)
   float* cm_ml = reinterpret_cast<float*>(smem + 80 * 1024);  // [4 warps][16][2]
   for (int rg = 0; rg < rows_here; rg += 16) {
   const int rg_n = min(16, rows_here - rg);
-  if (p.wide_merge) {
-    for (int rr0 = 0; rr0 < rg_n; rr0 += 4) {
-      const int nr = min(4, rg_n - rr0);
-      float4 acc4[4];
-      float mm4[4], ll4[4];
-      split_merge_rows4<ROWS>(po, pml, p.splits_full, warp, lane, rg + rr0, nr, acc4, mm4, ll4);
+  // four rows per pass: 16 independent 512 B loads in flight per warp (split_merge_rows4); the row-at-a-time loop it
+  // replaced cost splits/16 dependent L2 round trips per row (~25 us of a single-retrieval-head launch)
+  for (int rr0 = 0; rr0 < rg_n; rr0 += 4) {
+    const int nr = min(4, rg_n - rr0);
+    float4 acc4[4];
+    float mm4[4], ll4[4];
+    split_merge_rows4<ROWS>(po, pml, p.splits_full, warp, lane, rg + rr0, nr, acc4, mm4, ll4);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q < nr) {
-          *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr0 + q) * 128 + lane * 4]) = acc4[q];
-          if (lane == 0) {
-            cm_ml[(warp * 16 + rr0 + q) * 2] = mm4[q];
-            cm_ml[(warp * 16 + rr0 + q) * 2 + 1] = ll4[q];
-          }
+    for (int q = 0; q < 4; ++q) {
+      if (q < nr) {
+        *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr0 + q) * 128 + lane * 4]) = acc4[q];
+        if (lane == 0) {
+          cm_ml[(warp * 16 + rr0 + q) * 2] = mm4[q];
+          cm_ml[(warp * 16 + rr0 + q) * 2 + 1] = ll4[q];
         }
       }
-    }
-  } else
-  for (int rr = 0; rr < rg_n; ++rr) {
-    const int r = rg + rr;
-    float mm = -INFINITY, ll = 0.f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = warp; s0 < p.splits_full; s0 += 16) {
-      float ms[4], ls[4];
-      float4 vs[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int s2 = s0 + 4 * u;
-        const bool ok = s2 < p.splits_full;
-        const int sc2 = ok ? s2 : s0;
-        ms[u] = ok ? __ldcg(&pml[(sc2 * ROWS + r) * 2]) : -INFINITY;
-        ls[u] = __ldcg(&pml[(sc2 * ROWS + r) * 2 + 1]);
-        vs[u] = __ldcg(reinterpret_cast<const float4*>(&po[((long long)sc2 * ROWS + r) * 128 + lane * 4]));
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (ms[u] == -INFINITY) continue;
-        const float mn = fmaxf(mm, ms[u]);
-        const float fo = (mm == -INFINITY) ? 0.f : fast_exp2(mm - mn);
-        const float fn = fast_exp2(ms[u] - mn);
-        acc.x = acc.x * fo + vs[u].x * fn;
-        acc.y = acc.y * fo + vs[u].y * fn;
-        acc.z = acc.z * fo + vs[u].z * fn;
-        acc.w = acc.w * fo + vs[u].w * fn;
-        ll = ll * fo + ls[u] * fn;
-        mm = mn;
-      }
-    }
-    *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr) * 128 + lane * 4]) = acc;
-    if (lane == 0) {
-      cm_ml[(warp * 16 + rr) * 2] = mm;
-      cm_ml[(warp * 16 + rr) * 2 + 1] = ll;
     }
   }
   __syncthreads();
@@ -572,17 +535,7 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   p.cache_scan = (int)std::min<long long>(p.W, st->total);
 
   // split the retrieval heads' keys so that the grid covers ~2 CTAs per SM
-  int sm_count = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    static int cached_dev = -1, cached_sms = 148;
-    if (cached_dev != dev) {
-      cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
-      cached_dev = dev;
-    }
-    sm_count = cached_sms;
-  }
+  const int sm_count = sm_count_current_device();
   const bool partial = part_o != nullptr;
   p.part_o = part_o;
   p.part_lse = part_lse;
@@ -623,16 +576,12 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
   p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
   p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
-  p.wide_merge = wide_merge_enabled() ? 1 : 0;
 
   const int grid_x = d.n_full * p.n_rb * splits + (partial ? 0 : d.n_stream * p.n_rb);
   if (grid_x == 0) return DUO_OK;
   auto kern = duo_attn_mma_kernel<T, KEY_WARPS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES));
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;  // per template instantiation, one bit per device
+  if (int rc = ensure_dyn_smem(kern, ATTN_SMEM_BYTES, &attr_mask)) return rc;
   // a layer without retrieval (or without streaming) heads still needs *some* valid descriptor object in
   // the parameter slot; it is never dereferenced because no CTA of that class is launched.
   const CUtensorMap& fk = L->has_full_maps ? L->maps.full_k64 : L->maps.ring_k64;

@@ -43,7 +43,6 @@ struct TcParams {
   int n_tok_items;   // token-tile items per (kv head, head item)
   int n_head_items;  // head items per kv head
   int pair_heads;    // 1: slots are two heads (G even); 0: slots are two token tiles (G odd)
-  int warp_arrive;   // EXPERIMENTAL (DUO_TC_WARP_ARRIVE=1): one p_full arrival per softmax warp instead of per thread
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -216,7 +215,7 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_init(&bars.v_full[s], 1);
       mbar_init(&bars.v_empty[s], 1);
       mbar_init(&bars.s_full[s], 1);
-      mbar_init(&bars.p_full[s], p.warp_arrive ? 4 : 128);
+      mbar_init(&bars.p_full[s], 128);
       mbar_init(&bars.o_done[s], 1);
     }
     fence_barrier_init();
@@ -343,7 +342,7 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int j = 0; j < n_tiles; ++j) {
       const long long j0 = tile_start(j);
       const long long jend = (j < nA) ? a1 : b1;
-      mbar_wait(&bars.s_full[slot], j & 1);
+      mbar_wait_spin(&bars.s_full[slot], j & 1);
       tc_fence_after();
       const bool cache_seg = (!is_full) && (j < nA);
       const bool need_mask = cache_seg || (j0 + TC_TILE > jend) || (j0 + TC_TILE - 1 > base + slot_tok0[slot]);
@@ -394,12 +393,7 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           l_run += rs;
           tmem_wait_st();
           tc_fence_before();
-          if (p.warp_arrive) {  // 128 arrivals on one mbarrier serialise; the path taken is warp-uniform (votes)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.p_full[slot]);
-          } else {
-            mbar_arrive(&bars.p_full[slot]);
-          }
+          mbar_arrive(&bars.p_full[slot]);  // (one arrival per warp instead of per thread measured no faster)
           continue;
         }
       }
@@ -437,7 +431,7 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           m_ref = mx;
           l_run *= alpha;
         }
-        mbar_wait(&bars.o_done[slot], (j - 1) & 1);  // PV(j-1) has finished accumulating into O
+        mbar_wait_spin(&bars.o_done[slot], (j - 1) & 1);  // PV(j-1) has finished accumulating into O
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -466,16 +460,11 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       l_run += rs;
       tmem_wait_st();
       tc_fence_before();
-      if (p.warp_arrive) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.p_full[slot]);
-      } else {
-        mbar_arrive(&bars.p_full[slot]);
-      }
+      mbar_arrive(&bars.p_full[slot]);
     }
 
     // ---- epilogue: O / l -> global ----------------------------------------------------------------
-    mbar_wait(&bars.o_done[slot], (n_tiles - 1) & 1);
+    mbar_wait_spin(&bars.o_done[slot], (n_tiles - 1) & 1);
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     T* dst = reinterpret_cast<T*>(p.out) + (long long)b * p.out_batch_stride +
@@ -545,13 +534,6 @@ int launch_attn_tc(const duo_layer* L, const duo_cache_state* st, const void* q,
     }
   }
   TcParams p{};
-  {
-    static const bool wa = [] {  // opt-in until validated on hardware
-      const char* e = getenv("DUO_TC_WARP_ARRIVE");
-      return e != nullptr && e[0] == '1';
-    }();
-    p.warp_arrive = wa ? 1 : 0;
-  }
   p.out = out;
   const int n_q = (d.n_full + d.n_stream) * d.group;
   p.out_batch_stride = (long long)q_len * n_q * kHeadDim;
@@ -586,19 +568,13 @@ int launch_attn_tc(const duo_layer* L, const duo_cache_state* st, const void* q,
   const CUtensorMap& rv = L->has_ring_maps ? L->maps.ring_v128 : L->maps.full_v128;
   if (d.dtype == DUO_DT_BF16) {
     auto kern = duo_attn_tc_kernel<__nv_bfloat16>;
-    static bool attr = false;
-    if (!attr) {
-      DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-      attr = true;
-    }
+    static unsigned long long attr_mask = 0;
+    if (int rc = ensure_dyn_smem(kern, TC_SMEM_BYTES, &attr_mask)) return rc;
     kern<<<dim3(grid_x, d.batch), TC_THREADS, TC_SMEM_BYTES, stream>>>(map_q, fk, fv, rk, rv, p);
   } else {
     auto kern = duo_attn_tc_kernel<__half>;
-    static bool attr = false;
-    if (!attr) {
-      DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-      attr = true;
-    }
+    static unsigned long long attr_mask = 0;
+    if (int rc = ensure_dyn_smem(kern, TC_SMEM_BYTES, &attr_mask)) return rc;
     kern<<<dim3(grid_x, d.batch), TC_THREADS, TC_SMEM_BYTES, stream>>>(map_q, fk, fv, rk, rv, p);
   }
   DUO_CUDA_TRY(cudaGetLastError());

@@ -251,20 +251,14 @@ int duo_allreduce_add_rmsnorm(const duo_comm* comm, const void* partial, const v
   const size_t smem = (size_t)d.hidden * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   if (d.dtype == DUO_DT_BF16) {
-    static bool attr = false;
-    if (!attr && smem > 48 * 1024) {
-      DUO_CUDA_TRY(cudaFuncSetAttribute(duo::ar_add_rmsnorm_kernel<__nv_bfloat16>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
+    static unsigned long long attr_mask = 0;
+    if (smem > 48 * 1024)
+      if (int rc = duo::ensure_dyn_smem(duo::ar_add_rmsnorm_kernel<__nv_bfloat16>, 64 * 1024, &attr_mask)) return rc;
     duo::ar_add_rmsnorm_kernel<__nv_bfloat16><<<rows, duo::kCommThreads, smem, s>>>(p);
   } else {
-    static bool attr = false;
-    if (!attr && smem > 48 * 1024) {
-      DUO_CUDA_TRY(cudaFuncSetAttribute(duo::ar_add_rmsnorm_kernel<__half>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
+    static unsigned long long attr_mask = 0;
+    if (smem > 48 * 1024)
+      if (int rc = duo::ensure_dyn_smem(duo::ar_add_rmsnorm_kernel<__half>, 64 * 1024, &attr_mask)) return rc;
     duo::ar_add_rmsnorm_kernel<__half><<<rows, duo::kCommThreads, smem, s>>>(p);
   }
   DUO_CUDA_TRY(cudaGetLastError());

@@ -74,7 +74,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a lost TMA transaction / missing arrival must not hang the GPU.  After 2^26 failed polls (a failed
+// try_wait suspends the thread for an implementation-defined interval first, so this is seconds to a minute) the
+// kernel traps, which surfaces as a CUDA launch failure (DUO_ECUDA at the next API call) instead of a wedged device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls == (1u << 26)) asm volatile("trap;");
+  }
+}
+// Unbounded spin for register-starved consumers whose producer side is already bounded (a trap anywhere ends the grid).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
@@ -174,10 +184,10 @@ __device__ __forceinline__ bool stream_slot_valid(int j, int sink, int recent, l
   return p >= lo;
 }
 
-// Split-KV merge, wide variant (EXPERIMENTAL, DUO_WIDE_MERGE=1): one warp merges its share of the `splits` partials
-// (splits warp, warp+4, ...) for up to FOUR rows at once, i.e. 16 independent 512-byte loads in flight per iteration
-// instead of 4.  The row-at-a-time loop costs splits/16 dependent L2 round trips PER ROW, which dominates a
-// decode launch that has a single retrieval head (~290 splits: ~25 us of a ~75 us kernel).
+// Split-KV merge: one warp merges its share of the `splits` partials (splits warp, warp+4, ...) for up to FOUR rows
+// at once, i.e. 16 independent 512-byte loads in flight per iteration.  (A row-at-a-time loop costs splits/16
+// dependent L2 round trips PER ROW, which dominated decode launches with a single retrieval head: measured on the
+// B200 box, 1M-token decode 10.80 -> 10.54 ms of attention per step, profiles/r2_validation.md.)
 //   po  : [splits][ROWS][128] un-normalised partial outputs, pml : [splits][ROWS][2] (max in log2 domain, sum)
 //   rows r0 .. r0+nr-1 (nr <= 4); results: acc[q] (this lane's 4 output dims), mm[q], ll[q]
 template <int ROWS>
@@ -225,6 +235,23 @@ __device__ __forceinline__ void split_merge_rows4(const float* po, const float* 
   }
 }
 
-bool wide_merge_enabled();  // api.cu: DUO_WIDE_MERGE=1
+
+// ---------------------------------------------------------------------------------------------
+// per-DEVICE launch attributes (one process may drive several GPUs, as the reference's tensor_parallel mode does,
+// duo_attn/utils.py:206-227: cudaFuncSetAttribute is per device, so the "already set" memo is a device bit mask)
+// ---------------------------------------------------------------------------------------------
+int sm_count_current_device();  // api.cu
+template <typename K>
+inline int ensure_dyn_smem(K kern, int bytes, unsigned long long* done_mask, bool max_carveout = false) {
+  int dev = 0;
+  DUO_CUDA_TRY(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return DUO_OK;
+  DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (max_carveout)
+    DUO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+  return DUO_OK;
+}
 
 }  // namespace duo

@@ -97,6 +97,12 @@ int launch_add_rmsnorm(const void* x, const void* residual, const void* weight, 
                        long long rows, int hidden, float eps, int dtype, cudaStream_t stream) {
   if (rows == 0) return DUO_OK;
   const size_t smem = (size_t)hidden * sizeof(float);
+  if (smem > 48 * 1024) {  // hidden > 12288 (the API accepts up to 16384 = 64 KB)
+    static unsigned long long mask_bf = 0, mask_h = 0;
+    const int rc = dtype == DUO_DT_BF16 ? ensure_dyn_smem(add_rmsnorm_kernel<__nv_bfloat16>, 64 * 1024, &mask_bf)
+                                        : ensure_dyn_smem(add_rmsnorm_kernel<__half>, 64 * 1024, &mask_h);
+    if (rc) return rc;
+  }
   if (dtype == DUO_DT_BF16) {
     add_rmsnorm_kernel<__nv_bfloat16><<<(unsigned)rows, 256, smem, stream>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)weight, (__nv_bfloat16*)out_norm,

@@ -346,6 +346,20 @@ __global__ void state_advance_kernel(long long* st, int n, int sink, int recent)
   }
 }
 
+__global__ void state_set_kernel(long long* st, long long full_len, long long total, long long lo) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st[0] = full_len;
+    st[1] = total;
+    st[2] = lo;
+  }
+}
+
+int launch_state_set(long long* st, long long full_len, long long total, long long lo, cudaStream_t stream) {
+  state_set_kernel<<<1, 32, 0, stream>>>(st, full_len, total, lo);
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
 int launch_state_advance(long long* st, int n, int sink, int recent, cudaStream_t stream) {
   state_advance_kernel<<<1, 32, 0, stream>>>(st, n, sink, recent);
   DUO_CUDA_TRY(cudaGetLastError());

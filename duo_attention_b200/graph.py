@@ -12,8 +12,6 @@ device tensor, so ONE captured step can be replayed for every generated token:
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 
@@ -22,10 +20,8 @@ class DuoDecodeGraph:
         if cache.growable:
             raise ValueError("DuoDecodeGraph needs a pre-allocated cache (DuoAttentionStaticKVCache): a growable "
                              "cache may be re-allocated, which would leave stale pointers in the captured graph")
-        if cache.kv_format != "same" and os.environ.get("DUO_EXPERIMENTAL") != "1":
-            raise ValueError("DuoDecodeGraph: INT4 caches are driven eagerly for now (the device-state path of the "
-                             "INT4 kernel has not been validated on hardware yet)")
         self.model, self.cache = model, cache
+        cache.graph_attached = True  # the captured launches hold raw buffer addresses: no re-allocation from now on
         dev = cache.device
         B = cache.batch_size
         cache.enable_device_state()
@@ -61,6 +57,11 @@ class DuoDecodeGraph:
 
     def step(self, token: torch.Tensor) -> torch.Tensor:
         """Run one decode step for ``token`` ([B,1] int64, device or pinned host)."""
+        c = self.cache
+        for l in range(c.num_layers):  # the capture-time overflow check does not re-run on replay: same error as eager
+            if c.num_full_kv_head_list[l] > 0 and c.kv_seq_len_list[l] + 1 > c.full_cap_list[l]:
+                raise ValueError(f"Trying to put 1 KVs into a cache with max size {c.full_cap_list[l]}, "
+                                 f"current size: {c.kv_seq_len_list[l]}.")
         self.ids.copy_(token, non_blocking=True)
         self.graph.replay()
         self.cache.advance_host(1)

@@ -109,6 +109,7 @@ class DuoKVCache:
         for l in range(num_layers):
             self.tensors.append(self._alloc_layer(l, self.full_cap_list[l], self.stage_cap_list[l]))
             self._make_handle(l)
+        self.graph_attached = False  # set by DuoDecodeGraph: buffers must then keep their addresses
         self.dev_state = None        # optional device copy of (full_len, total, lo): see enable_device_state()
         self.launch_count = 0        # kernels of this library enqueued through this cache
         self.profile_events = None   # set to [] to collect (start, end) CUDA events around every duo_attention
@@ -125,7 +126,8 @@ class DuoKVCache:
         """First staging slot (duo_b200.h): right after the ring, 64-aligned for INT4 caches."""
         return self.W if self.kv_format == "same" else (self.W + 63) // 64 * 64
 
-    def _alloc_layer(self, l, full_cap, stage_cap):
+    def _alloc_layer(self, l, full_cap, stage_cap, only=None):
+        """Allocate layer ``l``'s buffers; ``only="ring"`` allocates just the streaming-head tensors."""
         nf, ns = self.num_full_kv_head_list[l], self.num_streaming_kv_head_list[l]
         B, D, dev = self.batch_size, self.head_dim, self.device
         slots = self.stage_off + stage_cap
@@ -133,13 +135,14 @@ class DuoKVCache:
             slots = (slots + 7) // 8 * 8
             full_cap = (full_cap + 63) // 64 * 64
         t = {}
+        shapes = [(name, heads, rows) for name, heads, rows in (("full_k", nf, full_cap), ("full_v", nf, full_cap),
+                                                                ("ring_k", ns, slots), ("ring_v", ns, slots))
+                  if only is None or name.startswith(only)]
         if self.kv_format == "same":
-            for name, heads, rows in (("full_k", nf, full_cap), ("full_v", nf, full_cap),
-                                      ("ring_k", ns, slots), ("ring_v", ns, slots)):
+            for name, heads, rows in shapes:
                 t[name] = torch.zeros(B, heads, rows, D, dtype=self.dtype, device=dev)
         else:
-            for name, heads, rows in (("full_k", nf, full_cap), ("full_v", nf, full_cap),
-                                      ("ring_k", ns, slots), ("ring_v", ns, slots)):
+            for name, heads, rows in shapes:
                 t[name] = torch.zeros(B, heads, rows, D // 2, dtype=torch.uint8, device=dev)
                 t[name + "_scale"] = torch.zeros(B, heads, rows, dtype=torch.float16, device=dev)
                 t[name + "_zero"] = torch.zeros(B, heads, rows, dtype=torch.float16, device=dev)
@@ -194,15 +197,21 @@ class DuoKVCache:
         grow_stage = q_len > self.stage_cap_list[l]
         if not (grow_full or grow_stage):
             return
+        if self.graph_attached:
+            raise ValueError("this cache is captured in a DuoDecodeGraph: its buffers cannot be re-allocated "
+                             f"(chunk of {q_len} tokens > staging capacity {self.stage_cap_list[l]})")
         new_full = self.full_cap_list[l]
         if need_full > new_full:
             new_full = max(need_full, 2 * new_full, 256)
         new_stage = max(self.stage_cap_list[l], q_len)
         old = self.tensors[l]
-        new = self._alloc_layer(l, new_full, new_stage)
+        # only what must grow is re-allocated: a longer staging area leaves the (possibly multi-GB) retrieval cache alone
+        new = self._alloc_layer(l, new_full, new_stage, only=None if grow_full else "ring")
         n = self.kv_seq_len_list[l]
         for name, t in old.items():
-            if name.startswith("full"):
+            if name not in new:
+                new[name] = t
+            elif name.startswith("full"):
                 new[name][:, :, :n].copy_(t[:, :, :n])
             else:
                 new[name][:, :, : self.W].copy_(t[:, :, : self.W])
@@ -220,14 +229,16 @@ class DuoKVCache:
             self._scratch = sc
         return sc
 
-    # ---- EXPERIMENTAL (DUO_INT4_PREFILL_SCRATCH=1): large chunks over an INT4 cache on the tcgen05 kernel --------
+    # ---- large chunks (>= 128 tokens) over an INT4 cache: tcgen05 prefill kernel on an fp16 image ----------------
     def _dequant_scratch(self, l, S):
-        """fp16 image of layer ``l``'s INT4 cache for ONE attention call — literally what the reference does on every
-        call (``get()`` dequantises the whole cache, demo/int4_kv.py:373-436, then flash_attn_func runs on it,
-        demo/w8a8kv4_llama.py:239-274).  For a chunk of >= 128 tokens the O(ctx) dequantisation pass is noise next to
-        the chunk x ctx attention, and the attention then runs on the tensor-core prefill kernel instead of the
-        mma.sync INT4 kernel.  One flat fp16 buffer is shared by all layers (they are processed one after the other);
-        a layer handle is created per distinct number of retrieval heads."""
+        """fp16 image of layer ``l``'s INT4 cache for ONE attention call of a chunk of >= 128 tokens — what the
+        reference does on EVERY call (``get()`` dequantises the whole cache, demo/int4_kv.py:373-436, then
+        flash_attn_func runs on it, demo/w8a8kv4_llama.py:239-274).  For such a chunk the O(ctx) dequantisation pass
+        is < 1 % of the chunk x ctx attention, and the attention runs on the tensor-core prefill kernel (measured
+        on the box: INT4 128K prefill at the bf16 speed, profiles/r2_validation.md).  Decode and small chunks never
+        come here: their kernels dequantise in the K/V load stage.  One flat zero-initialised fp16 buffer is shared
+        by all layers (they are processed one after the other; rows beyond the dequantised range hold zeros or
+        finite leftovers and are masked); a layer handle is created per distinct number of retrieval heads."""
         sc = self.__dict__.get("_dq")
         B, D, Hkv = self.batch_size, self.head_dim, self.num_kv_heads
         cap = max(self.full_cap_list)
@@ -236,8 +247,8 @@ class DuoKVCache:
             nf_max = max(self.num_full_kv_head_list)
             ns_max = max(self.num_streaming_kv_head_list)
             sc = {"cap": cap, "slots": slots, "handles": {},
-                  "full": [torch.empty(B * nf_max * cap * D, dtype=self.dtype, device=self.device) for _ in range(2)],
-                  "ring": [torch.empty(B * ns_max * slots * D, dtype=self.dtype, device=self.device) for _ in range(2)]}
+                  "full": [torch.zeros(B * nf_max * cap * D, dtype=self.dtype, device=self.device) for _ in range(2)],
+                  "ring": [torch.zeros(B * ns_max * slots * D, dtype=self.dtype, device=self.device) for _ in range(2)]}
             old = self.__dict__.get("_dq")
             if old is not None:
                 for hd in old["handles"].values():
@@ -292,18 +303,18 @@ class DuoKVCache:
         boundaries, so one copy serves the whole cache."""
         if self.dev_state is None:
             self.dev_state = torch.zeros(4, dtype=torch.int64, device=self.device)
-            self._host_state = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.sync_device_state()
         return self
 
     def sync_device_state(self):
+        """Stream-ordered refresh of the device copy: the integers travel as kernel arguments (duo_state_set), so
+        back-to-back evict_last()/clear() calls cannot race through a shared staging buffer."""
         if self.dev_state is None:
             return
         l = self.num_layers - 1
-        self._host_state[0] = self.kv_seq_len_list[l]
-        self._host_state[1] = self.total_list[l]
-        self._host_state[2] = self.lo_list[l]
-        self.dev_state.copy_(self._host_state, non_blocking=True)
+        _C.check(self.lib.duo_state_set(self.dev_state.data_ptr(), self.kv_seq_len_list[l], self.total_list[l],
+                                        self.lo_list[l], torch.cuda.current_stream(self.device).cuda_stream))
+        self.launch_count += 1
 
     def advance_device(self, n):
         """Enqueue full_len += n, total += n, lo = max(lo, total - recent, sink) on the device copy."""
@@ -401,8 +412,7 @@ class DuoKVCache:
             _C.check(lib.duo_rope_append(ah, C.byref(ast), qkv.data_ptr(), qkv.stride(1), cp, sp,
                                          rope_mode | _C.ROPE_SKIP_Q, S, stream))
             self.launch_count += 1
-        elif (self.kv_format == "int4" and S >= 128 and self.W <= 2048 and not force_mma
-              and os.environ.get("DUO_INT4_PREFILL_SCRATCH") == "1"):
+        elif self.kv_format == "int4" and S >= 128 and self.W <= 2048 and not force_mma:
             ah, ast = self._dequant_scratch(l, S), _C.CacheState(st.full_len, st.total, st.lo, None)
         fn = lib.duo_attention_mma if force_mma else lib.duo_attention
         if self.profile_events is not None:

@@ -200,6 +200,13 @@ def shard_model(model, full_attention_heads, rank: int, world: int):
     cfg.num_key_value_heads = n_kv // world
     cfg.intermediate_size = inter // world
     shard = type(model)(cfg).to(next(model.parameters()).dtype)
+    # `.to(dtype)` also casts the rotary inverse frequencies; a checkpoint loaded with torch_dtype=bf16 keeps them in
+    # fp32 (non-persistent buffer computed at construction).  Take the source model's buffers so every shard rotates
+    # with exactly the angles of the single-GPU model (the error of bf16 frequencies grows with position).
+    src_rot, dst_rot = getattr(model.model, "rotary_emb", None), getattr(shard.model, "rotary_emb", None)
+    if src_rot is not None and dst_rot is not None:
+        for name, buf in src_rot.named_buffers(recurse=False):
+            dst_rot.register_buffer(name, buf.detach().clone(), persistent=False)
     shard.model.embed_tokens.weight.copy_(model.model.embed_tokens.weight)
     shard.model.norm.weight.copy_(model.model.norm.weight)
     shard.lm_head.weight.copy_(model.lm_head.weight)

@@ -178,6 +178,9 @@ DUO_API int duo_attention_mma(const duo_layer* layer, const duo_cache_state* st,
 
 /* device_state += n tokens: full_len += n, total += n, lo = max(lo, total - recent, sink) (one tiny kernel). */
 DUO_API int duo_state_advance(int64_t* device_state, int32_t n, int32_t sink, int32_t recent, void* stream);
+/* device_state := {full_len, total, lo}, stream-ordered (the three integers travel as kernel arguments, so repeated
+ * evict_last()/clear() calls need no staging buffer and cannot race with earlier copies still in flight). */
+DUO_API int duo_state_set(int64_t* device_state, int64_t full_len, int64_t total, int64_t lo, void* stream);
 
 /* Move the tail of the staged chunk into sink/ring slots (call after duo_attention). */
 DUO_API int duo_stream_commit(const duo_layer* layer, const duo_cache_state* st, int32_t q_len, void* stream);

@@ -294,14 +294,15 @@ def int4_attention_core(q, k, v, past, n_full, groups, sink, recent):
     return tuple_attention_core(q, kq, vq, past, n_full, groups, sink, recent)
 
 
-def tuple_forward(w: AttnWeights, hidden, cos, sin, past, sink, recent):
-    """llama.py:146-306.  hidden ``[B,S,hidden]``; cos/sin ``[B,S,D]`` in hidden.dtype."""
+def tuple_forward(w: AttnWeights, hidden, cos, sin, past, sink, recent, core=None):
+    """llama.py:146-306.  hidden ``[B,S,hidden]``; cos/sin ``[B,S,D]`` in hidden.dtype.  ``core``: the attention
+    core after RoPE (default tuple_attention_core; int4_attention_core for the INT4-KV demo forward)."""
     B, S, _ = hidden.shape
     q = _lin(hidden, w.wq, w.bq).view(B, S, w.num_heads, w.head_dim)
     k = _lin(hidden, w.wk, w.bk).view(B, S, w.num_kv_heads, w.head_dim)
     v = _lin(hidden, w.wv, w.bv).view(B, S, w.num_kv_heads, w.head_dim)
     q, k = apply_rotary_pos_emb_hf(q, k, cos, sin, unsqueeze_dim=2)
-    out, new_past = tuple_attention_core(q, k, v, past, w.n_full, w.groups, sink, recent)
+    out, new_past = (core or tuple_attention_core)(q, k, v, past, w.n_full, w.groups, sink, recent)
     out = out.reshape(B, S, w.num_heads * w.head_dim)
     return _lin(out, w.wo, w.bo), new_past
 
@@ -479,9 +480,11 @@ class OracleModel:
     """Llama/Mistral decoder run the way the reference's patched HF-4.34-style driver runs
     it.  Holds plain tensors copied from an (un-patched) HF model plus the head pattern."""
 
-    def __init__(self, hf_model, full_attention_heads, sink, recent):
+    def __init__(self, hf_model, full_attention_heads, sink, recent, kv_format="same"):
         cfg = hf_model.config
         self.cfg = cfg
+        # "int4": every layer's attention core is the INT4-KV one (demo/w8a8kv4_llama.py:215-278)
+        self.core = int4_attention_core if kv_format == "int4" else None
         self.sink, self.recent = sink, recent
         self.num_heads = cfg.num_attention_heads
         self.num_kv_heads = cfg.num_key_value_heads
@@ -526,7 +529,7 @@ class OracleModel:
             res = h
             x = rms_norm(h, L["ln1"], self.eps)
             past = None if past_key_values is None else past_key_values[idx]
-            a, p = tuple_forward(L["attn"], x, cos, sin, past, self.sink, self.recent)
+            a, p = tuple_forward(L["attn"], x, cos, sin, past, self.sink, self.recent, core=self.core)
             new_past.append(p)
             h = res + a
             res = h

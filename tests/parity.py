@@ -5,37 +5,76 @@ IS FlashAttention-2, and FA2 itself does not meet that bar element-for-element a
 restatement: P is rounded to bf16 block by block against the *running* max, so a few elements land up to a couple
 of bf16 ulps away (measured on the B200 box with the installed flash_attn 2.8.3 vs oracle.flash_attn_contract:
 0 violations for ordinary logits, 2.7e-4 of the elements — max |err| 0.0156 — when the softmax is sharp; see
-DESIGN.md §Parity).  The gate is therefore:
-
-  * at least 99.5 % of the elements within rtol=1e-2 / atol=1e-3, and
-  * no element outside rtol=2e-2 / atol=8e-3 (two bf16 ulps of an O(1) output),
-
-i.e. the stated tolerance with the slack two independently-rounded bf16-P pipelines need: with only a few tens
-of visible keys the rounding of P (relative 2^-9 per element, uncorrelated between the split-KV kernel and the
-single-block oracle) leaves ~0.3 % of near-zero outputs a hair (<= 2e-3) past atol.  That the kernels are not
-LESS accurate than the reference's kernel is asserted separately against an fp64 ground truth
-(tests/test_gpu_oracle_pin.py::test_accuracy_vs_fp64_truth_not_worse_than_flash_attn).
+DESIGN.md §Parity).  The gate is therefore expressed RELATIVE TO THE REFERENCE'S OWN KERNEL wherever that kernel can run on
+the test's inputs (`assert_parity(..., fa2=...)`): the number of our elements outside rtol=1e-2 / atol=1e-3 may exceed
+FlashAttention-2's own count against the same oracle output by at most max(0.1 % of the elements, 2 elements — the
+granularity of a 512-element decode output), and we may have no element outside rtol=2e-2 / atol=8e-3 (two bf16
+ulps of an O(1) output) that FA2 does not have.  Where FA2 cannot produce the comparison (INT4 caches — the
+reference dequantises first —, kernel-family-vs-kernel-family checks) the absolute gate applies: at least 99.5 % of
+the elements inside the tolerance (2 elements for tiny outputs) and none outside the hard bound.  Every call appends
+the achieved counts to gpurun_out/parity_log.jsonl (summarised in profiles/r2_parity.md).  That the kernels are not
+LESS accurate than the reference's kernel is also asserted against an fp64 ground truth
+(tests/test_gpu_oracle_pin.py::test_accuracy_vs_fp64_truth_not_worse_than_flash_attn, tests/test_gpu_bench_shapes.py).
 """
+import json
+import math
+import os
+
 import torch
 
 RTOL, ATOL = 1e-2, 1e-3
 MAX_VIOLATION_FRACTION = 5e-3
 HARD_RTOL, HARD_ATOL = 2e-2, 8e-3
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOG_PATH = os.environ.get("DUO_PARITY_LOG", os.path.join(_ROOT, "gpurun_out", "parity_log.jsonl"))
 
 
-def assert_parity(got: torch.Tensor, ref: torch.Tensor, what: str = ""):
+def record(kind: str, **fields):
+    """Append one JSON line per parity measurement (achieved violation fractions, errors) — kept under profiles/."""
+    try:
+        os.makedirs(os.path.dirname(LOG_PATH), exist_ok=True)
+        with open(LOG_PATH, "a") as f:
+            f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "kind": kind, **fields}) + "\n")
+    except OSError:
+        pass
+
+
+def _counts(x, ref):
+    err = (x - ref).abs()
+    viol = err > (ATOL + RTOL * ref.abs())
+    hard = err > (HARD_ATOL + HARD_RTOL * ref.abs())
+    return err, int(viol.sum().item()), int(hard.sum().item())
+
+
+def assert_parity(got: torch.Tensor, ref: torch.Tensor, what: str = "", fa2: torch.Tensor = None):
+    """``got`` (the CUDA product) against ``ref`` (oracle / reference output) at the north_star tolerance.
+
+    ``fa2``: output of the reference's own attention kernel (installed flash_attn_func) on the SAME inputs, when the
+    test can produce it.  The gate is then relative: our violation count may exceed FlashAttention-2's own count
+    against the same ``ref`` by at most max(1e-3 of the elements, 2 elements), and we may have no hard-bound
+    violation that FA2 does not have.  Without ``fa2`` (INT4 caches, GPU-vs-GPU comparisons) the absolute gate of the
+    header applies.  Every call logs what was achieved (``record``)."""
     got, ref = got.float(), ref.float()
     assert got.shape == ref.shape, (got.shape, ref.shape)
     assert torch.isfinite(got).all(), f"{what}: non-finite output"
-    err = (got - ref).abs()
-    viol = err > (ATOL + RTOL * ref.abs())
-    frac = viol.float().mean().item()
-    hard = err > (HARD_ATOL + HARD_RTOL * ref.abs())
-    allowed = max(MAX_VIOLATION_FRACTION, 8.0 / viol.numel())  # small tensors: a handful of elements
-    if frac > allowed or hard.any():
+    n = got.numel()
+    err, n_viol, n_hard = _counts(got, ref)
+    frac = n_viol / n
+    if fa2 is not None:
+        fa2 = fa2.float().to(ref.device)
+        e2, fa2_viol, fa2_hard = _counts(fa2, ref)
+        allowed, hard_allowed = fa2_viol + max(math.ceil(1e-3 * n), 2), fa2_hard
+        rule = f"FlashAttention-2's own {fa2_viol} + eps"
+        record("parity", what=what, n=n, viol=n_viol, hard=n_hard, max_err=err.max().item(), fa2_viol=fa2_viol,
+               fa2_hard=fa2_hard, fa2_max_err=e2.max().item())
+    else:
+        allowed, hard_allowed = max(math.ceil(MAX_VIOLATION_FRACTION * n), 2), 0
+        rule = f"{MAX_VIOLATION_FRACTION:.0e} of the elements"
+        record("parity", what=what, n=n, viol=n_viol, hard=n_hard, max_err=err.max().item())
+    if n_viol > allowed or n_hard > hard_allowed:
         idx = tuple(int(i) for i in torch.nonzero(err == err.max())[0])
         raise AssertionError(
-            f"{what}: {frac:.2e} of elements outside rtol={RTOL}/atol={ATOL} (allowed {MAX_VIOLATION_FRACTION:.0e}), "
-            f"{int(hard.sum())} outside the hard bound; max |err| {err.max().item():.5f} at {idx} "
+            f"{what}: {n_viol} of {n} elements ({frac:.2e}) outside rtol={RTOL}/atol={ATOL} (allowed {allowed}: {rule}), "
+            f"{n_hard} outside the hard bound (allowed {hard_allowed}); max |err| {err.max().item():.5f} at {idx} "
             f"(got {got[idx].item():.5f}, ref {ref[idx].item():.5f})")
     return err.max().item(), frac

@@ -25,9 +25,53 @@ def split_qkv(qkv, Hq, Hkv):
     return q, k, v
 
 
+class Fa2Shadow:
+    """The reference forward's attention core (llama.py:225-290) with the INSTALLED flash_attn_func on token-major GPU
+    caches, fed the same chunks as the product: gives every parity assertion FlashAttention-2's own deviation from
+    the oracle on the same inputs (tests/parity.py).  None when flash_attn is not importable."""
+
+    def __init__(self, n_full, groups, sink, recent):
+        try:
+            from flash_attn import flash_attn_func
+        except Exception:
+            flash_attn_func = None
+        self.fa = flash_attn_func
+        self.n_full, self.G, self.sink, self.recent = n_full, groups, sink, recent
+        self.kv = None
+
+    def step(self, q, k, v):
+        if self.fa is None:
+            return None
+        nf, G = self.n_full, self.G
+        q, k, v = q.cuda(), k.cuda(), v.cuda()
+        if self.kv is None:
+            out = self.fa(q, k, v, causal=True)
+            fk, fv, sk, sv = k[:, :, :nf], v[:, :, :nf], k[:, :, nf:], v[:, :, nf:]
+        else:
+            fk, fv, sk, sv = self.kv
+            fk, fv = torch.cat([fk, k[:, :, :nf]], 1), torch.cat([fv, v[:, :, :nf]], 1)
+            sk, sv = torch.cat([sk, k[:, :, nf:]], 1), torch.cat([sv, v[:, :, nf:]], 1)
+            parts = []
+            if nf > 0:
+                parts.append(self.fa(q[:, :, : nf * G], fk, fv, causal=True))
+            if nf * G < q.shape[2]:
+                parts.append(self.fa(q[:, :, nf * G :], sk, sv, causal=True))
+            out = torch.cat(parts, dim=2)
+        if sk.shape[1] > self.sink + self.recent:
+            sk = torch.cat([sk[:, : self.sink], sk[:, sk.shape[1] - self.recent :]], 1)
+            sv = torch.cat([sv[:, : self.sink], sv[:, sv.shape[1] - self.recent :]], 1)
+        self.kv = (fk, fv, sk, sv)
+        return out.float().cpu()
+
+    def evict(self, n):
+        if self.kv is not None:
+            self.kv = tuple(t[:, : t.shape[1] - n] for t in self.kv)
+
+
 def run_schedule(Hq, Hkv, n_full, sink, recent, chunks, B=1, dtype=torch.bfloat16, seed=0, evict_after=None,
                  force_mma=False, max_size=None, stage_cap=8, check=True, qscale=1.0):
     dev = torch.device("cuda:0")
+    shadow = Fa2Shadow(n_full, Hq // Hkv, sink, recent) if check else None
     g = torch.Generator().manual_seed(seed)
     total = sum(chunks)
     cache = DuoKVCache(1, Hq, Hkv, D, [n_full], B, max_size or total + 8, sink, recent, dtype, dev,
@@ -45,11 +89,13 @@ def run_schedule(Hq, Hkv, n_full, sink, recent, chunks, B=1, dtype=torch.bfloat1
         got = out.float().cpu()
         outs.append(got)
         if check:
-            assert_parity(got, ref, f"chunk {i} (len {S}, past {cache.kv_seq_len - S})")
+            assert_parity(got, ref, f"chunk {i} (len {S}, past {cache.kv_seq_len - S})", fa2=shadow.step(q, k, v))
         worst = max(worst, (got - ref.float()).abs().max().item())
         ev = (evict_after or {}).get(i, 0)
         if ev:
             cache.evict_last(ev)
+            if shadow is not None:
+                shadow.evict(ev)
             fk, sk = past
             past = (fk[:, :, : fk.shape[2] - ev].contiguous(), sk[:, :, : sk.shape[2] - ev].contiguous())
         assert cache.kv_seq_len == past[0].shape[2]

@@ -62,3 +62,59 @@ def test_int4_cache_content_is_k1_quantisation():
     assert np.array_equal(t["full_k"][0, 0, :10].cpu().numpy(), p[0])
     assert np.array_equal(t["full_k_scale"][0, 0, :10].cpu().numpy(), s[0, :, 0])
     assert np.array_equal(t["full_k_zero"][0, 0, :10].cpu().numpy(), z[0, :, 0])
+
+
+def test_int4_many_splits():
+    """> 16 splits per retrieval head: the split-KV merge loop takes more than one pass per warp."""
+    run(4, 1, 1, 64, 256, [20000, 1, 2, 1], seed=16, stage_cap=20000)
+
+
+def test_int4_batch2_decode():
+    run(8, 2, 1, 8, 24, [3000, 1, 2, 1, 1], seed=17, B=2, stage_cap=3000)
+
+
+def test_int4_mha_rows_up_to_8():
+    """group 1: q_len 1..8 all fit the 8-row (keys-as-M) decode kernel; 9..16 the row-major one."""
+    run(4, 4, 2, 4, 12, [50, 1, 8, 7, 5, 1, 3, 9, 16, 1], seed=18, stage_cap=50)
+
+
+def test_int4_large_chunks_batch2():
+    """Chunks of >= 128 tokens after the first call run on the tcgen05 kernel over a dequantised fp16 image of the
+    cache (kv_cache._dequant_scratch) and must match the oracle's dequantise-everything attention."""
+    run(8, 2, 1, 16, 48, [300, 130, 1, 256, 1, 2, 128, 1], seed=19, B=2, stage_cap=300)
+    run(8, 2, 0, 16, 48, [200, 129, 1, 140], seed=20, stage_cap=200)   # no retrieval head in the layer
+    run(8, 2, 2, 16, 48, [200, 129, 1, 140], seed=21, stage_cap=200)   # no streaming head in the layer
+
+
+def test_int4_large_chunk_kernel_families_agree():
+    """The same >= 128-token chunk through the mma.sync INT4 kernel (dequant in the load stage) and through the
+    tcgen05 kernel on the fp16 image."""
+    dev = torch.device("cuda:0")
+    Hq, Hkv, n_full = 8, 2, 1
+    outs = []
+    for force in (False, True):
+        g = torch.Generator().manual_seed(23)
+        cache = DuoKVCache(1, Hq, Hkv, D, [n_full], 1, 2048, 16, 48, torch.float16, dev, stage_cap=700, kv_format="int4")
+        res = []
+        for S in [700, 384, 1, 200]:
+            qkv = torch.randn(1, S, (Hq + 2 * Hkv) * D, generator=g).to(torch.float16).to(dev)
+            out = torch.empty(1, S, Hq, D, dtype=torch.float16, device=dev)
+            if force and cache.kv_seq_len > 0:
+                # duo_attention on the INT4 layer handle itself = the mma.sync INT4 kernel
+                import ctypes as C
+                st = cache.state(0)
+                stream = torch.cuda.current_stream().cuda_stream
+                cache._ensure_room(0, S)
+                _C.check(cache.lib.duo_rope_append(cache.handles[0], C.byref(st), qkv.data_ptr(), qkv.stride(1), None,
+                                                   None, _C.ROPE_NONE, S, stream))
+                _C.check(cache.lib.duo_attention(cache.handles[0], C.byref(st), qkv.data_ptr(), qkv.stride(1),
+                                                 out.data_ptr(), S, D ** -0.5, cache.workspace.data_ptr(),
+                                                 cache.workspace.numel(), stream))
+                _C.check(cache.lib.duo_stream_commit(cache.handles[0], C.byref(st), S, stream))
+                cache.advance(0, S)
+            else:
+                cache.attend(0, qkv, None, None, _C.ROPE_NONE, out)
+            res.append(out.float().cpu())
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert_parity(a, b, "INT4 chunk: tcgen05-on-fp16-image vs mma.sync fused-dequant kernel")

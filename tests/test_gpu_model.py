@@ -141,3 +141,80 @@ def test_cuda_graph_decode_matches_eager_decode():
                 ca.evict_last(1)
                 cb.evict_last(1)
                 graph.resync()
+
+
+def test_int4_cuda_graph_decode_matches_eager():
+    """Device-resident occupancy (dstate) path of the INT4 decode kernels: graph replay == eager, token by token."""
+    from duo_attention_b200.graph import DuoDecodeGraph
+
+    model = tiny_model("llama", seed=7).to(torch.float16)
+    gates = np.array([[1.0, 0.0], [0.0, 1.0]])
+    sink, recent = 4, 6
+    enable_llama_duo_attention_static_kv_cache_eval(model, gates)
+    model.cuda()
+    ca = DuoAttentionStaticKVCache(model, gates, 1, 256, sink, recent, kv_format="int4")
+    cb = DuoAttentionStaticKVCache(model, gates, 1, 256, sink, recent, kv_format="int4")
+    g = torch.Generator().manual_seed(4)
+    ids = torch.randint(0, 512, (1, 37), generator=g).cuda()
+    with torch.no_grad():
+        model(input_ids=ids, past_key_values=ca, use_cache=True)
+        model(input_ids=ids, past_key_values=cb, use_cache=True)
+        graph = DuoDecodeGraph(model, cb)
+        toks = torch.randint(0, 512, (20, 1, 1), generator=g).cuda()
+        for i in range(20):
+            want = model(input_ids=toks[i], past_key_values=ca, use_cache=True).logits
+            got = graph.step(toks[i])
+            torch.testing.assert_close(got.float(), want.float(), rtol=0, atol=0, msg=lambda m: f"step {i}: {m}")
+            if i == 9:
+                ca.evict_last(1)
+                cb.evict_last(1)
+                graph.resync()
+
+
+def test_int4_model_through_the_drop_in_cache_class():
+    """Model level, INT4 KV: enable_*_static_kv_cache_eval + DuoAttentionStaticINT4KVCache (the demo's class name and
+    constructor, demo/int4_kv.py:115-260) vs the oracle model whose attention core restates
+    demo/w8a8kv4_llama.py:215-278 (first call raw fp16, later calls the quantise->dequantise round trip)."""
+    from duo_attn.patch import DuoAttentionStaticINT4KVCache
+
+    model = tiny_model("llama", seed=11).to(torch.float16)
+    gates = np.array([[1.0, 0.0], [1.0, 1.0]])
+    sink, recent = 8, 16
+    oracle = O.OracleModel(copy.deepcopy(model), gates, sink, recent, kv_format="int4")
+    enable_llama_duo_attention_static_kv_cache_eval(model, gates)
+    model.cuda()
+    cache = DuoAttentionStaticINT4KVCache(model, gates, 1, 512, sink, recent, 160)
+    g = torch.Generator().manual_seed(5)
+    past_o = None
+    with torch.no_grad():
+        for S in [150, 1, 1, 140, 1, 33, 1, 1]:  # 140: a >= 128-token chunk over an INT4 cache (tcgen05 on the fp16 image)
+            ids = torch.randint(0, 512, (1, S), generator=g)
+            lo, past_o = oracle(ids, past_o)
+            out = model(input_ids=ids.cuda(), past_key_values=cache, use_cache=True)
+            torch.testing.assert_close(out.logits.float().cpu(), lo, rtol=5e-2, atol=5e-2)
+            assert cache.kv_seq_len == past_o[0][0].shape[2]
+    assert cache.memory_usage > 0
+
+
+def test_graph_step_raises_when_the_cache_is_full():
+    """Replaying the captured step past the capacity must raise the reference's ValueError (static_kv_cache.py:112-115),
+    not write past the allocation."""
+    from duo_attention_b200.graph import DuoDecodeGraph
+
+    model = tiny_model("llama", seed=9)
+    gates = np.array([[1.0, 0.0], [0.0, 1.0]])
+    enable_llama_duo_attention_static_kv_cache_eval(model, gates)
+    model.cuda()
+    cache = DuoAttentionStaticKVCache(model, gates, 1, 40, 4, 6)
+    ids = torch.randint(0, 512, (1, 37)).cuda()
+    with torch.no_grad():
+        model(input_ids=ids, past_key_values=cache, use_cache=True)
+        graph = DuoDecodeGraph(model, cache)
+        tok = torch.zeros(1, 1, dtype=torch.long, device="cuda")
+        for _ in range(3):
+            graph.step(tok)
+        assert cache.kv_seq_len == 40
+        with pytest.raises(ValueError, match="Trying to put 1 KVs into a cache with max size 40"):
+            graph.step(tok)
+        with pytest.raises(ValueError, match="captured in a DuoDecodeGraph"):
+            model(input_ids=torch.zeros(1, 100, dtype=torch.long).cuda(), past_key_values=cache, use_cache=True)
