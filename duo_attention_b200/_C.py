@@ -22,7 +22,8 @@ DECODE_MAX_Q = 16
 SYMBOLS = [
     "duo_layer_create", "duo_layer_destroy", "duo_workspace_bytes", "duo_rope_append", "duo_attention",
     "duo_attention_mma", "duo_state_advance", "duo_state_set", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
-    "duo_attention_partial", "duo_merge_partials",
+    "duo_attention_partial", "duo_merge_partials", "duo_attention_seq",
+    "duo_seqcomm_data_bytes", "duo_seqcomm_flag_bytes", "duo_seqcomm_create", "duo_seqcomm_destroy", "duo_seq_merge",
     "duo_comm_data_bytes", "duo_comm_flag_bytes", "duo_comm_create", "duo_comm_destroy", "duo_allreduce_add_rmsnorm",
     "duo_last_error_string", "duo_version",
 ]
@@ -42,7 +43,13 @@ class LayerDesc(C.Structure):
 
 
 class CacheState(C.Structure):
-    _fields_ = [("full_len", C.c_int64), ("total", C.c_int64), ("lo", C.c_int64), ("device_state", C.c_void_p)]
+    _fields_ = [("full_len", C.c_int64), ("total", C.c_int64), ("lo", C.c_int64), ("device_state", C.c_void_p),
+                ("seq_rank", C.c_int32), ("seq_world", C.c_int32), ("seq_block", C.c_int32), ("seq_reserved", C.c_int32)]
+
+
+class SeqCommDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("local_state", C.c_void_p),
+                ("rank", C.c_int32), ("world", C.c_int32), ("max_rows", C.c_int32)]
 
 
 class CommDesc(C.Structure):
@@ -94,6 +101,18 @@ def load():
     lib.duo_silu_mul.restype = C.c_int
     lib.duo_attention_partial.argtypes = [vp, i64, vp, i64, vp, vp, i32, f32, vp, sz, vp]
     lib.duo_attention_partial.restype = C.c_int
+    lib.duo_attention_seq.argtypes = [vp, C.POINTER(CacheState), vp, i64, vp, vp, vp, i32, f32, vp, sz, vp]
+    lib.duo_attention_seq.restype = C.c_int
+    lib.duo_seqcomm_data_bytes.argtypes = [i32, i32]
+    lib.duo_seqcomm_data_bytes.restype = sz
+    lib.duo_seqcomm_flag_bytes.argtypes = [i32, i32]
+    lib.duo_seqcomm_flag_bytes.restype = sz
+    lib.duo_seqcomm_create.argtypes = [C.POINTER(SeqCommDesc), C.POINTER(vp)]
+    lib.duo_seqcomm_create.restype = C.c_int
+    lib.duo_seqcomm_destroy.argtypes = [vp]
+    lib.duo_seqcomm_destroy.restype = None
+    lib.duo_seq_merge.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.duo_seq_merge.restype = C.c_int
     lib.duo_merge_partials.argtypes = [vp, vp, i32, i64, i32, i32, vp, i32, vp]
     lib.duo_merge_partials.restype = C.c_int
     lib.duo_comm_data_bytes.argtypes = [i32, i32, i32, i32]

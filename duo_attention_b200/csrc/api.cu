@@ -58,6 +58,9 @@ int launch_dequant_int4(const void* packed, const void* scale, const void* zero,
 int launch_attn_mma_partial(const duo_layer* L, long long n_keys, const void* q, long long q_row_stride, float* out_o,
                             float* out_lse, int q_len, float scale, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream);
+int launch_attn_mma_seq(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
+                        float* part_o, float* part_lse, int q_len, float scale, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
 int launch_merge_partials(const float* o_parts, const float* lse_parts, int n_parts, long long tokens, int heads_total,
                           int heads_used, void* out, int dtype, cudaStream_t stream);
 int launch_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res,
@@ -208,7 +211,19 @@ static int check_chunk(const duo_layer* L, const duo_cache_state* st, int q_len,
     set_error("%s: negative cache state", who);
     return DUO_EINVAL;
   }
-  if (L->d.n_full > 0 && st->full_len + q_len > L->d.full_cap) {
+  long long need = st->full_len + q_len;
+  if (st->seq_world != 0) {
+    if (st->seq_world < 2 || st->seq_world > 8 || st->seq_rank < 0 || st->seq_rank >= st->seq_world || st->seq_block < 1) {
+      set_error("%s: bad sequence-shard descriptor (rank %d, world %d, block %d)", who, st->seq_rank, st->seq_world,
+                st->seq_block);
+      return DUO_EINVAL;
+    }
+    const long long round = (long long)st->seq_block * st->seq_world, rem = need % round;
+    long long extra = rem - (long long)st->seq_rank * st->seq_block;
+    extra = extra < 0 ? 0 : (extra > st->seq_block ? st->seq_block : extra);
+    need = need / round * st->seq_block + extra;  // rows of this rank's slice after the append
+  }
+  if (L->d.n_full > 0 && need > L->d.full_cap) {
     set_error("Trying to put %d KVs into a cache with max size %lld, current size: %lld.", q_len,
               (long long)L->d.full_cap, (long long)st->full_len);
     return DUO_EOVERFLOW;
@@ -245,6 +260,10 @@ int duo_attention(const duo_layer* layer, const duo_cache_state* st, const void*
   if (rc) return rc;
   if (!q || !out) {
     set_error("duo_attention: null buffer");
+    return DUO_EINVAL;
+  }
+  if (st->seq_world != 0) {
+    set_error("duo_attention: sequence-sharded caches are attended with duo_attention_seq");
     return DUO_EINVAL;
   }
   if (layer->d.kv_format == DUO_KV_INT4)
@@ -323,6 +342,28 @@ int duo_attention_partial(const duo_layer* layer, int64_t n_keys, const void* q,
   }
   return launch_attn_mma_partial(layer, n_keys, q, q_row_stride, out_o, out_lse, q_len, scale, workspace,
                                  workspace_bytes, (cudaStream_t)stream);
+}
+
+int duo_attention_seq(const duo_layer* layer, const duo_cache_state* st, const void* q, int64_t q_row_stride, void* out,
+                      float* out_o, float* out_lse, int32_t q_len, float scale, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  int rc = check_chunk(layer, st, q_len, "duo_attention_seq");
+  if (rc) return rc;
+  if (!q || !out || !out_o || !out_lse) {
+    set_error("duo_attention_seq: null buffer");
+    return DUO_EINVAL;
+  }
+  if (st->seq_world < 2) {
+    set_error("duo_attention_seq: the cache state carries no sequence-shard descriptor");
+    return DUO_EINVAL;
+  }
+  if (layer->d.kv_format != DUO_KV_SAME || layer->d.group * q_len > 16) {
+    set_error("duo_attention_seq: 16-bit caches and group * q_len <= 16 only (got group %d, q_len %d)", layer->d.group,
+              q_len);
+    return DUO_EINVAL;
+  }
+  return launch_attn_mma_seq(layer, st, q, q_row_stride, out, out_o, out_lse, q_len, scale, workspace, workspace_bytes,
+                             (cudaStream_t)stream);
 }
 
 int duo_merge_partials(const float* o_parts, const float* lse_parts, int32_t n_parts, int64_t tokens,

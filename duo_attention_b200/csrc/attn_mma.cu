@@ -47,12 +47,26 @@ struct AttnParams {
   float* ws_o;           // [batch][n_full][n_rb][splits][ROWS][128]
   float* ws_ml;          // [batch][n_full][n_rb][splits][ROWS][2]
   int* counters;         // [batch][n_full][n_rb]
-  // partial mode (duo_attention_partial): fp32 normalised O + log2-domain log-sum-exp per (token, q head) instead of
-  // `out`; every query row sees all `full_len` keys (no causal offset); only retrieval heads are launched
+  // partial mode (duo_attention_partial / duo_attention_seq): retrieval heads write the fp32 normalised O + log2-domain
+  // log-sum-exp of THIS slice of their cache per (token, q head) instead of `out`.
+  //   no_causal = 1 (duo_attention_partial): every query row sees all `full_len` keys; only retrieval heads launched
+  //   seq_world > 1 (duo_attention_seq): `full_len` counts GLOBAL tokens, the layer's retrieval cache holds the
+  //       block-cyclic slice of rank seq_rank (position p lives on rank (p / seq_block) % seq_world, slice order ==
+  //       position order); token t sees the local rows of positions <= full_len + t; streaming heads run normally
   float* part_o;
   float* part_lse;
   int no_causal;
+  int seq_rank, seq_world, seq_block;
 };
+
+// rows of the block-cyclic slice of `rank` that hold positions < n  (host twin: seqshard.SeqShardPlan.local_len)
+__host__ __device__ __forceinline__ long long seq_local_len(long long n, int rank, int world, int block) {
+  const long long round = (long long)block * world;
+  const long long full_rounds = n / round, rem = n % round;
+  long long extra = rem - (long long)rank * block;
+  extra = extra < 0 ? 0 : (extra > block ? block : extra);
+  return full_rounds * block + extra;
+}
 
 template <typename T, int KEY_WARPS>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
@@ -64,7 +78,8 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     p.full_len = pin.dstate[0];
     p.total = pin.dstate[1];
     p.lo = pin.dstate[2];
-    const long long nk = p.full_len + p.q_len;
+    const long long nk = p.seq_world > 1 ? seq_local_len(p.full_len + p.q_len, p.seq_rank, p.seq_world, p.seq_block)
+                                         : p.full_len + p.q_len;
     long long kps = (nk + p.splits_full - 1) / p.splits_full;
     kps = (kps + TILE - 1) / TILE * TILE;
     p.keys_per_split = (int)(kps < TILE ? TILE : kps);
@@ -112,19 +127,19 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
 
   // key segments [a0,a1) (cache) and [b0,b1) (staged chunk, streaming heads only)
   long long a0, a1, b0 = 0, b1 = 0;
-  long long base;  // key j visible to token t  <=>  j <= base + t
+  // number of keys (of this CTA's key index space) visible to token t: key j is visible  <=>  j < vis_count(t)
+  auto vis_count = [&](int t) -> long long {
+    if (!is_full) return (long long)p.W + t + 1;
+    if (p.no_causal) return p.full_len;
+    if (p.seq_world > 1) return seq_local_len(p.full_len + t + 1, p.seq_rank, p.seq_world, p.seq_block);
+    return p.full_len + t + 1;
+  };
   if (is_full) {
-    base = p.full_len;
-    long long nkeys = p.full_len + tok_max + 1;
-    if (p.no_causal) {
-      base = 1LL << 60;
-      nkeys = p.full_len;
-    }
+    const long long nkeys = vis_count(tok_max);
     a0 = (long long)split * p.keys_per_split;
     a1 = min(nkeys, a0 + (long long)p.keys_per_split);
     if (a1 < a0) a1 = a0;
   } else {
-    base = p.W;
     a0 = 0;
     a1 = p.cache_scan;
     b0 = p.W;
@@ -188,6 +203,9 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     }
   }
 
+  const long long lim_r[2] = {tok_r[0] >= 0 ? vis_count(tok_r[0]) : 0, tok_r[1] >= 0 ? vis_count(tok_r[1]) : 0};
+  const long long lim_min = vis_count((row0 + wrow) / p.group);  // smallest limit among this warp's rows
+
   float o[16][4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -228,8 +246,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
 
     // ---- mask + online softmax ----------------------------------------------------------------
     const long long kfirst = j0 + wkey;
-    const int tmin = (row0 + wrow) / p.group;
-    const bool need_mask = (kfirst + KPW > jend) || (kfirst + KPW - 1 > base + tmin) ||
+    const bool need_mask = (kfirst + KPW > jend) || (kfirst + KPW > lim_min) ||
                            (!is_full && i < nA);  // rows beyond rows_here hold q == 0 and are never stored
     if (need_mask) {
 #pragma unroll
@@ -237,8 +254,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const long long j = kfirst + n * 8 + 2 * t4 + (e & 1);
-          const int tk = tok_r[e >> 1];
-          bool vis = (tk >= 0) && (j < jend) && (j <= base + tk);
+          bool vis = (j < jend) && (j < lim_r[e >> 1]);
           if (!is_full && j < p.W) vis = vis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
           if (!vis) sc[n][e] = -INFINITY;
         }
@@ -390,7 +406,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     const int R = row0 + r;
     const int tok = R / p.group;
     const int hq = kvh * p.group + R % p.group;
-    if (p.part_o) {
+    if (p.part_o && is_full) {
       float* dst = p.part_o + (((long long)b * p.q_len + tok) * p.n_q_heads + hq) * kHeadDim + d;
       *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
       return;
@@ -411,7 +427,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
       const float l = sm_ml[r * 2 + 1];
       const float inv = l > 0.f ? 1.f / l : 0.f;
       store_row_elem(r, d, sm_o[r * 128 + d] * inv, sm_o[r * 128 + d + 1] * inv);
-      if (p.part_lse && d == 0) store_row_lse(r, sm_ml[r * 2], l);
+      if (p.part_lse && is_full && d == 0) store_row_lse(r, sm_ml[r * 2], l);
     }
     return;
   }
@@ -502,10 +518,16 @@ size_t mma_workspace_bytes(int batch, int n_kv, int group, int max_q_len) {
   return (size_t)(o + ml + cnt + 4096);
 }
 
+struct PartialMode {      // how the retrieval heads report (see AttnParams)
+  float* part_o = nullptr;
+  float* part_lse = nullptr;
+  bool no_causal = false;  // duo_attention_partial: plain slice, streaming heads not launched
+};
+
 template <typename T, int KEY_WARPS>
 static int launch_variant(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride,
                           void* out, int q_len, float scale, void* workspace, size_t workspace_bytes,
-                          cudaStream_t stream, float* part_o = nullptr, float* part_lse = nullptr) {
+                          cudaStream_t stream, PartialMode pm = PartialMode()) {
   const duo_layer_desc& d = L->d;
   constexpr int ROWS = 16 * (4 / KEY_WARPS);
   AttnParams p{};
@@ -536,11 +558,16 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
 
   // split the retrieval heads' keys so that the grid covers ~2 CTAs per SM
   const int sm_count = sm_count_current_device();
-  const bool partial = part_o != nullptr;
-  p.part_o = part_o;
-  p.part_lse = part_lse;
-  p.no_causal = partial ? 1 : 0;
-  const long long nkeys = partial ? st->full_len : st->full_len + q_len;
+  const bool partial = pm.no_causal;  // slice-only launch: no streaming CTAs
+  p.part_o = pm.part_o;
+  p.part_lse = pm.part_lse;
+  p.no_causal = pm.no_causal ? 1 : 0;
+  p.seq_rank = st->seq_rank;
+  p.seq_world = st->seq_world;
+  p.seq_block = st->seq_block;
+  const long long nkeys = partial ? st->full_len
+                          : st->seq_world > 1 ? seq_local_len(st->full_len + q_len, st->seq_rank, st->seq_world, st->seq_block)
+                                              : st->full_len + q_len;
   int splits = 1;
   if (d.n_full > 0) {
     const int budget = 2 * sm_count;
@@ -659,11 +686,29 @@ int launch_attn_mma_partial(const duo_layer* L, long long n_keys, const void* q,
   st.total = 0;
   st.lo = L->d.sink;
   st.device_state = nullptr;
+  PartialMode pm;
+  pm.part_o = out_o;
+  pm.part_lse = out_lse;
+  pm.no_causal = true;
   if (L->d.dtype == DUO_DT_BF16)
     return launch_variant<__nv_bfloat16, 4>(L, &st, q, q_row_stride, nullptr, q_len, scale, workspace, workspace_bytes,
-                                            stream, out_o, out_lse);
+                                            stream, pm);
   return launch_variant<__half, 4>(L, &st, q, q_row_stride, nullptr, q_len, scale, workspace, workspace_bytes, stream,
-                                   out_o, out_lse);
+                                   pm);
+}
+
+// Sequence-sharded decode step (duo_attention_seq): retrieval heads attend this rank's slice and report (O, lse)
+// partials, streaming heads (replicated on every rank) write their final rows of `out`.
+int launch_attn_mma_seq(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
+                        float* part_o, float* part_lse, int q_len, float scale, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
+  PartialMode pm;
+  pm.part_o = part_o;
+  pm.part_lse = part_lse;
+  if (L->d.dtype == DUO_DT_BF16)
+    return launch_variant<__nv_bfloat16, 4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes,
+                                            stream, pm);
+  return launch_variant<__half, 4>(L, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes, stream, pm);
 }
 
 }  // namespace duo

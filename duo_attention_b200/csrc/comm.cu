@@ -18,11 +18,16 @@
 // needs every peer's k+1 flag, which a peer only sends after it has finished reading call k).  One CTA per row, rows
 // <= max_rows (decode and small chunks; large prefill chunks are bandwidth-bound and stay on NCCL).
 //
-// EXPERIMENTAL: not validated on hardware yet; the host side only uses it when DUO_FUSED_ALLREDUCE=1 (tp.py).
+//
+// The same push / flag / wait primitive carries the exchange step of the sequence-sharded decode (seq_merge_kernel
+// below): (O, log-sum-exp) partials of the retrieval heads instead of hidden-state rows.
 #include "duo_common.cuh"
 
 struct duo_comm {
   duo_comm_desc d;
+};
+struct duo_seqcomm {
+  duo_seqcomm_desc d;
 };
 
 namespace duo {
@@ -177,6 +182,93 @@ __global__ void __launch_bounds__(kCommThreads) ar_add_rmsnorm_kernel(const Comm
   if (tid == 0) p.state[row] = (int)epoch;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sequence-sharded decode: exchange + merge of the retrieval heads' partial attention.  One CTA of 128 threads per
+// (token, retrieval q-head) row; payload per row and sender = 128 fp32 outputs + the log-sum-exp, padded to 132 floats.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSeqRowFloats = 132;
+
+struct SeqMergeParams {
+  float* peer_data[kMaxWorld];
+  unsigned int* peer_flags[kMaxWorld];
+  const float* part_o;
+  const float* part_lse;
+  void* out;
+  int* state;
+  int rank, world, max_rows, heads_total, heads_used;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) seq_merge_kernel(const SeqMergeParams p) {
+  __shared__ int s_epoch;
+  __shared__ float s_w[kMaxWorld];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int tok = row / p.heads_used, h = row % p.heads_used;
+  const long long src_row = (long long)tok * p.heads_total + h;
+  if (tid == 0) s_epoch = p.state[row] + 1;
+  __syncthreads();
+  const unsigned int epoch = (unsigned int)s_epoch;
+  const int slot = (int)(epoch & 1u);
+  // ---- 1. push my partial row to every rank (posted 4-byte stores, 512 B coalesced per peer) -------------------
+  {
+    const float v = p.part_o[src_row * kHeadDim + tid];
+    const float l = p.part_lse[src_row];
+    const long long off = (((long long)slot * p.world + p.rank) * p.max_rows + row) * kSeqRowFloats;
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q) {
+      if (q < p.world) {
+        p.peer_data[q][off + tid] = v;
+        if (tid == 0) p.peer_data[q][off + kHeadDim] = l;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 2. publish / 3. wait (bounded) ----------------------------------------------------------------------------
+  if (tid < p.world) {
+    __threadfence_system();
+    unsigned int* f = nullptr;
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+      if (q == tid) f = p.peer_flags[q];
+    st_release_sys(f + (long long)row * p.world + p.rank, epoch);
+    unsigned int* mine = nullptr;
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+      if (q == p.rank) mine = p.peer_flags[q];
+    const unsigned int* w = mine + (long long)row * p.world + tid;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(w) - epoch) < 0) {
+      if (clock64() - t0 > 6000000000LL) {  // ~3 s
+        p.state[p.max_rows] = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 4. merge the `world` partials in rank order: out = sum_s 2^(lse_s - max) o_s / sum_s 2^(lse_s - max) -----------
+  const float* my_data = nullptr;
+#pragma unroll
+  for (int q = 0; q < kMaxWorld; ++q)
+    if (q == p.rank) my_data = p.peer_data[q];
+  const float* base = my_data + ((long long)slot * p.world * p.max_rows + row) * kSeqRowFloats;
+  const long long sstride = (long long)p.max_rows * kSeqRowFloats;
+  if (tid < p.world) s_w[tid] = __ldcg(base + tid * sstride + kHeadDim);
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int s2 = 0; s2 < p.world; ++s2) mx = fmaxf(mx, s_w[s2]);
+  float acc = 0.f, wsum = 0.f;
+  for (int s2 = 0; s2 < p.world; ++s2) {
+    const float l = s_w[s2];
+    if (l == -INFINITY) continue;
+    const float w = fast_exp2(l - mx);
+    acc += w * __ldcg(base + s2 * sstride + tid);
+    wsum += w;
+  }
+  const float v = wsum > 0.f ? acc / wsum : 0.f;
+  reinterpret_cast<T*>(p.out)[src_row * kHeadDim + tid] = CmCvt<T>::from_f(v);
+  if (tid == 0) p.state[row] = (int)epoch;
+}
+
 static size_t elt_bytes(int dtype) { return (dtype == DUO_DT_BF16 || dtype == DUO_DT_FP16) ? 2 : 0; }
 
 }  // namespace duo
@@ -261,6 +353,80 @@ int duo_allreduce_add_rmsnorm(const duo_comm* comm, const void* partial, const v
       if (int rc = duo::ensure_dyn_smem(duo::ar_add_rmsnorm_kernel<__half>, 64 * 1024, &attr_mask)) return rc;
     duo::ar_add_rmsnorm_kernel<__half><<<rows, duo::kCommThreads, smem, s>>>(p);
   }
+  DUO_CUDA_TRY(cudaGetLastError());
+  return DUO_OK;
+}
+
+size_t duo_seqcomm_data_bytes(int32_t world, int32_t max_rows) {
+  if (world < 1 || max_rows < 1) return 0;
+  return (size_t)2 * world * max_rows * duo::kSeqRowFloats * sizeof(float);
+}
+
+size_t duo_seqcomm_flag_bytes(int32_t world, int32_t max_rows) { return duo_comm_flag_bytes(world, max_rows); }
+
+int duo_seqcomm_create(const duo_seqcomm_desc* desc, duo_seqcomm** out) {
+  if (!desc || !out) {
+    duo::set_error("duo_seqcomm_create: null argument");
+    return DUO_EINVAL;
+  }
+  const duo_seqcomm_desc& d = *desc;
+  if (d.world < 2 || d.world > duo::kMaxWorld || d.rank < 0 || d.rank >= d.world || d.max_rows < 1 || d.max_rows > 512 ||
+      !d.local_state) {
+    duo::set_error("duo_seqcomm_create: bad descriptor (world %d, rank %d, max_rows %d)", d.world, d.rank, d.max_rows);
+    return DUO_EINVAL;
+  }
+  for (int r = 0; r < d.world; ++r) {
+    if (!d.data[r] || !d.flags[r] || (reinterpret_cast<uintptr_t>(d.data[r]) & 15) ||
+        (reinterpret_cast<uintptr_t>(d.flags[r]) & 3)) {
+      duo::set_error("duo_seqcomm_create: peer buffer %d missing or misaligned", r);
+      return DUO_EINVAL;
+    }
+  }
+  duo_seqcomm* c = new duo_seqcomm;
+  c->d = d;
+  *out = c;
+  return DUO_OK;
+}
+
+void duo_seqcomm_destroy(duo_seqcomm* comm) { delete comm; }
+
+int duo_seq_merge(const duo_seqcomm* comm, const float* part_o, const float* part_lse, void* out, int32_t tokens,
+                  int32_t heads_total, int32_t heads_used, int32_t dtype, void* stream) {
+  if (!comm || tokens < 0 || heads_total < 1 || heads_used < 0 || heads_used > heads_total ||
+      (dtype != DUO_DT_BF16 && dtype != DUO_DT_FP16)) {
+    duo::set_error("duo_seq_merge: bad argument");
+    return DUO_EINVAL;
+  }
+  const int rows = tokens * heads_used;
+  if (rows == 0) return DUO_OK;
+  if (!part_o || !part_lse || !out) {
+    duo::set_error("duo_seq_merge: null buffer");
+    return DUO_EINVAL;
+  }
+  const duo_seqcomm_desc& d = comm->d;
+  if (rows > d.max_rows) {
+    duo::set_error("duo_seq_merge: %d rows exceed the communicator's max_rows %d", rows, d.max_rows);
+    return DUO_EOVERFLOW;
+  }
+  duo::SeqMergeParams p{};
+  for (int r = 0; r < d.world; ++r) {
+    p.peer_data[r] = reinterpret_cast<float*>(d.data[r]);
+    p.peer_flags[r] = reinterpret_cast<unsigned int*>(d.flags[r]);
+  }
+  p.part_o = part_o;
+  p.part_lse = part_lse;
+  p.out = out;
+  p.state = reinterpret_cast<int*>(d.local_state);
+  p.rank = d.rank;
+  p.world = d.world;
+  p.max_rows = d.max_rows;
+  p.heads_total = heads_total;
+  p.heads_used = heads_used;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DUO_DT_BF16)
+    duo::seq_merge_kernel<__nv_bfloat16><<<rows, 128, 0, s>>>(p);
+  else
+    duo::seq_merge_kernel<__half><<<rows, 128, 0, s>>>(p);
   DUO_CUDA_TRY(cudaGetLastError());
   return DUO_OK;
 }

@@ -82,6 +82,7 @@ struct RopeAppendParams {
   long long full_cap, full_len;
   const long long* dstate;
   int kv_int4;
+  int seq_rank, seq_world, seq_block;  // sequence-sharded retrieval caches (duo_cache_state): append owned positions only
   void *full_k, *full_v, *ring_k, *ring_v;
   __half *fks, *fkz, *fvs, *fvz, *rks, *rkz, *rvs, *rvz;
 };
@@ -144,9 +145,15 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const RopeAppendParams
   const bool full = h < p.n_full;
   long long dst_row;  // row index inside the destination tensor
   const long long full_len = p.dstate ? p.dstate[0] : p.full_len;
-  if (full)
-    dst_row = ((long long)b * p.n_full + h) * p.full_cap + full_len + t;
-  else
+  if (full) {
+    long long row = full_len + t;
+    if (p.seq_world > 1) {  // block-cyclic slice: position -> (owner, local row); other ranks' positions are skipped
+      const long long blk = row / p.seq_block;
+      if ((int)(blk % p.seq_world) != p.seq_rank) return;
+      row = (blk / p.seq_world) * p.seq_block + row % p.seq_block;
+    }
+    dst_row = ((long long)b * p.n_full + h) * p.full_cap + row;
+  } else
     dst_row = ((long long)b * p.n_stream + (h - p.n_full)) * p.ring_slots + p.W + t;
   void* base = full ? (is_k ? p.full_k : p.full_v) : (is_k ? p.ring_k : p.ring_v);
   if (!p.kv_int4) {
@@ -180,6 +187,9 @@ int launch_rope_append(const duo_layer* L, const duo_cache_state* st, void* qkv,
   p.full_len = st->full_len;
   p.dstate = reinterpret_cast<const long long*>(st->device_state);
   p.kv_int4 = d.kv_format == DUO_KV_INT4;
+  p.seq_rank = st->seq_rank;
+  p.seq_world = st->seq_world;
+  p.seq_block = st->seq_block;
   p.full_k = d.full_k;
   p.full_v = d.full_v;
   p.ring_k = d.ring_k;

@@ -59,8 +59,8 @@ class DuoDecodeGraph:
         """Run one decode step for ``token`` ([B,1] int64, device or pinned host)."""
         c = self.cache
         for l in range(c.num_layers):  # the capture-time overflow check does not re-run on replay: same error as eager
-            if c.num_full_kv_head_list[l] > 0 and c.kv_seq_len_list[l] + 1 > c.full_cap_list[l]:
-                raise ValueError(f"Trying to put 1 KVs into a cache with max size {c.full_cap_list[l]}, "
+            if c.num_full_kv_head_list[l] > 0 and c._rows_needed(l, 1) > c.full_cap_list[l]:
+                raise ValueError(f"Trying to put 1 KVs into a cache with max size {c.max_size}, "
                                  f"current size: {c.kv_seq_len_list[l]}.")
         self.ids.copy_(token, non_blocking=True)
         self.graph.replay()

@@ -74,6 +74,7 @@ class DuoKVCache:
         stage_cap: int = 64,
         kv_format: str = "same",
         growable: bool = False,
+        local_full_cap: Optional[int] = None,
     ):
         device = torch.device(device)
         if device.type != "cuda":
@@ -102,7 +103,8 @@ class DuoKVCache:
         self.kv_seq_len_list = [0] * num_layers   # retrieval cache length
         self.total_list = [0] * num_layers        # tokens seen by the streaming heads
         self.lo_list = [self.sink_size] * num_layers
-        self.full_cap_list = [self.max_size] * num_layers
+        # rows actually allocated per retrieval head (== max_size unless a subclass shards the positions over ranks)
+        self.full_cap_list = [self.max_size if local_full_cap is None else int(local_full_cap)] * num_layers
         self.stage_cap_list = [max(1, int(stage_cap))] * num_layers
         self.tensors: List[dict] = []
         self.handles: List[Optional[int]] = [None] * num_layers
@@ -186,12 +188,12 @@ class DuoKVCache:
     def _ensure_room(self, l, q_len):
         """Grow the staging area (always allowed) and, for growable caches (tuple-path compatibility,
         where the reference simply torch.cat's), the retrieval cache."""
-        need_full = self.kv_seq_len_list[l] + q_len
+        need_full = self._rows_needed(l, q_len)
         grow_full = need_full > self.full_cap_list[l]
         if grow_full and not self.growable:
             # same check and message as static_kv_cache.py:112-115
             raise ValueError(
-                f"Trying to put {q_len} KVs into a cache with max size {self.full_cap_list[l]}, "
+                f"Trying to put {q_len} KVs into a cache with max size {self.max_size}, "
                 f"current size: {self.kv_seq_len_list[l]}."
             )
         grow_stage = q_len > self.stage_cap_list[l]
@@ -295,6 +297,10 @@ class DuoKVCache:
     def state(self, l) -> _C.CacheState:
         ds = self.dev_state.data_ptr() if self.dev_state is not None else None
         return _C.CacheState(self.kv_seq_len_list[l], self.total_list[l], self.lo_list[l], ds)
+
+    def _rows_needed(self, l, q_len) -> int:
+        """Rows of the (local) retrieval cache in use after appending ``q_len`` tokens."""
+        return self.kv_seq_len_list[l] + q_len
 
     # ---- device-resident occupancy (CUDA-graph replay of decode steps) ---------------------------------
     def enable_device_state(self):
@@ -455,6 +461,127 @@ class DuoAttentionStaticKVCache(DuoKVCache):
             kv_format=kv_format,
             growable=False,
         )
+
+
+class DuoSeqShardKVCache(DuoKVCache):
+    """Decode-phase cache of the SEQUENCE-SHARDED tensor-parallel layout (scope row f1; ``tp.install_seq_shard``):
+    every rank holds all heads of a layer, but of each retrieval head only its block-cyclic slice of the token
+    positions (``seqshard.SeqShardPlan``); streaming heads are replicated.  ``kv_seq_len`` keeps counting GLOBAL tokens.
+
+    ``attend`` = duo_rope_append (appends only positions this rank owns) -> duo_attention_seq (slice partials for the
+    retrieval heads, streaming heads final) -> duo_seq_merge (peer-memory exchange + merge) -> duo_stream_commit.
+    Only decode-sized chunks (group x q_len <= 16): prefill runs head-parallel and ``tp.reshard_heads_to_seq`` moves
+    the caches over (``load_from_head_parallel``).  Same ``clear`` / ``evict_last`` / ``memory_usage`` surface as the
+    static cache; ``DuoDecodeGraph`` can capture it."""
+
+    def __init__(self, model, full_attention_heads, batch_size, max_size, sink_size, recent_size, seq=None):
+        from .seqshard import SeqShardPlan
+
+        seq = seq if seq is not None else model._duo_seq
+        self.seq = seq
+        self.plan = SeqShardPlan(seq.world, seq.block)
+        p = next(model.parameters())
+        cfg = model.config
+        head_dim = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+        super().__init__(
+            num_layers=cfg.num_hidden_layers, num_heads=cfg.num_attention_heads, num_kv_heads=cfg.num_key_value_heads,
+            head_dim=head_dim, num_full_kv_head_list=[_count_full(r) for r in full_attention_heads],
+            batch_size=batch_size, max_size=max_size, sink_size=sink_size, recent_size=recent_size, dtype=p.dtype,
+            device=p.device, stage_cap=_C.DECODE_MAX_Q, kv_format="same", growable=False,
+            local_full_cap=self.plan.capacity(int(max_size)) + 1)
+        q_max = _C.DECODE_MAX_Q // self.num_kv_groups
+        if q_max < 1 or batch_size * q_max * self.num_heads > seq.comm.max_rows * 8:
+            pass  # the per-call row check in duo_seq_merge is authoritative
+        self.max_q = max(1, q_max)
+        self.part_o = torch.zeros(batch_size, self.max_q, self.num_heads, head_dim, dtype=torch.float32, device=p.device)
+        self.part_lse = torch.zeros(batch_size, self.max_q, self.num_heads, dtype=torch.float32, device=p.device)
+
+    def state(self, l) -> _C.CacheState:
+        st = super().state(l)
+        st.seq_rank, st.seq_world, st.seq_block = self.seq.rank, self.seq.world, self.seq.block
+        return st
+
+    def _rows_needed(self, l, q_len) -> int:
+        return self.plan.local_len(self.seq.rank, self.kv_seq_len_list[l] + q_len)
+
+    def attend(self, l, qkv, cos, sin, rope_mode, out, scale=None, force_mma=False):
+        if not qkv.is_cuda or not out.is_cuda:
+            raise RuntimeError("duo_attention_b200 kernels need CUDA tensors (no CPU fallback)")
+        B, S, width = qkv.shape
+        if S > self.max_q:
+            raise ValueError(f"sequence-sharded caches serve decode-sized chunks (<= {self.max_q} tokens, got {S}): "
+                             "prefill head-parallel and move the caches over with load_from_head_parallel()")
+        assert B == self.batch_size and width == (self.num_heads + 2 * self.num_kv_heads) * self.head_dim
+        assert qkv.stride(2) == 1 and (B == 1 or qkv.stride(0) == S * qkv.stride(1))
+        assert out.is_contiguous() and qkv.dtype == self.dtype and out.dtype == self.dtype
+        self._ensure_room(l, S)
+        st = self.state(l)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        h, lib = self.handles[l], self.lib
+        if scale is None:
+            scale = self.head_dim ** -0.5
+        cp = cos.data_ptr() if cos is not None else None
+        sp = sin.data_ptr() if sin is not None else None
+        _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode, S, stream))
+        nfq = self.num_full_kv_head_list[l] * self.num_kv_groups
+        po, pl = self.part_o[:, :S], self.part_lse[:, :S]
+        if S != self.max_q:  # the kernels index [batch][q_len][heads]: contiguous views of the right q_len
+            po = self.part_o.view(-1)[: B * S * self.num_heads * self.head_dim].view(B, S, self.num_heads, self.head_dim)
+            pl = self.part_lse.view(-1)[: B * S * self.num_heads].view(B, S, self.num_heads)
+        if self.profile_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _C.check(lib.duo_attention_seq(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), po.data_ptr(),
+                                       pl.data_ptr(), S, float(scale), self.workspace.data_ptr(),
+                                       self.workspace.numel(), stream))
+        if self.profile_events is not None:
+            e1.record()
+            self.profile_events.append((e0, e1))
+        if nfq:
+            self.seq.comm.merge(po, pl, out, B * S, self.num_heads, nfq)
+        _C.check(lib.duo_stream_commit(h, C.byref(st), S, stream))
+        self.launch_count += 2 + (1 if nfq else 0) + (1 if self.num_streaming_kv_head_list[l] > 0 else 0)
+        self.advance(l, S)
+        return out
+
+    def load_from_head_parallel(self, hp_cache: "DuoKVCache", head_plan, group=None):
+        """Take over the contents of a head-parallel cache (this rank's heads, all positions — what the prefill
+        phase filled) by point-to-point resharding; streaming rings are all-gathered (they are tiny)."""
+        import torch.distributed as dist
+
+        from . import tp
+
+        rank, world = self.seq.rank, self.seq.world
+        W = self.W
+        for l in range(self.num_layers):
+            n = hp_cache.kv_seq_len_list[l]
+            mask_row = head_plan.mask[l]
+            owners = head_plan.owners[l]
+            for name in ("full_k", "full_v"):
+                if self.tensors[l][name].numel():
+                    tp.reshard_heads_to_seq(hp_cache.tensors[l][name], owners, mask_row, rank, world, n, self.seq.block,
+                                            self.tensors[l][name], group)
+            stream_ids = [h for h in range(len(mask_row)) if mask_row[h] <= 0.5]
+            sidx = {h: i for i, h in enumerate(stream_ids)}
+            for name in ("ring_k", "ring_v"):
+                if not self.tensors[l][name].numel():
+                    continue
+                n_loc = max(len([h for h in owners[r] if mask_row[h] <= 0.5]) for r in range(world))
+                mine = [h for h in owners[rank] if mask_row[h] <= 0.5]
+                send = torch.zeros((self.batch_size, n_loc, W, self.head_dim), dtype=self.dtype, device=self.device)
+                if mine:
+                    send[:, : len(mine)] = hp_cache.tensors[l][name][:, :, :W]
+                got = [torch.empty_like(send) for _ in range(world)]
+                dist.all_gather(got, send, group=group)
+                for r in range(world):
+                    theirs = [h for h in owners[r] if mask_row[h] <= 0.5]
+                    for i, h in enumerate(theirs):
+                        self.tensors[l][name][:, sidx[h], :W] = got[r][:, i]
+            self.kv_seq_len_list[l] = n
+            self.total_list[l] = hp_cache.total_list[l]
+            self.lo_list[l] = hp_cache.lo_list[l]
+        self.sync_device_state()
+        return self
 
 
 class DuoAttentionStaticINT4KVCache(DuoAttentionStaticKVCache):

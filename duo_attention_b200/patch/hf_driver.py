@@ -137,6 +137,7 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
     cos, sin = cos[0].contiguous(), sin[0].contiguous()
     h = inputs_embeds.contiguous() if input_ids is not None else inputs_embeds.clone()  # updated in place below
     tp_on = getattr(self, "_duo_tp", False)
+    seq_on = getattr(self, "_duo_seq", None) is not None  # sequence-sharded decode: attention output needs no exchange
     if tp_on:
         from ..tp import all_reduce_sum
     layers = list(base.layers)
@@ -150,7 +151,7 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
 
         def reduce_add_norm(part, res, w, eps):
             """sum over ranks (if TP) + residual add + RMSNorm: one fused peer-memory kernel for small exchanges
-            (experimental, DUO_FUSED_ALLREDUCE=1), otherwise NCCL all-reduce followed by duo_add_rmsnorm."""
+            (tp.FusedAllReduce), otherwise NCCL all-reduce followed by duo_add_rmsnorm."""
             if comm is not None:
                 return comm.add_rmsnorm(part, res, w, eps)
             if tp_on:  # row-parallel partials -> one all-reduce per site (NCCL over NVLink)
@@ -161,7 +162,10 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
         for idx, layer in enumerate(layers):
             a = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
             ln2 = layer.post_attention_layernorm
-            x, h = reduce_add_norm(a, h, ln2.weight, ln2.variance_epsilon)
+            if seq_on:  # merged attention output is already complete (and bit-identical) on every rank
+                x, h = ops.add_rmsnorm(a, h, ln2.weight, ln2.variance_epsilon)
+            else:
+                x, h = reduce_add_norm(a, h, ln2.weight, ln2.variance_epsilon)
             m = _mlp_forward(layer.mlp, x)
             if idx + 1 < len(layers):
                 nxt = layers[idx + 1].input_layernorm
@@ -180,7 +184,7 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
             res = h
             x = layer.input_layernorm(h)
             x = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
-            if tp_on:
+            if tp_on and not seq_on:
                 x = all_reduce_sum(x, self._duo_tp_group)
             h = res + x
             res = h

@@ -129,6 +129,14 @@ typedef struct duo_cache_state {
    * above must then be upper-bound-consistent (they size the launch and drive the capacity checks).
    * duo_state_advance moves the device copy forward after a step. */
   const int64_t* device_state;
+  /* Sequence sharding of the retrieval heads across tensor-parallel ranks (scope row f1; all zero = off).  With
+   * seq_world > 1 the layer's full_k/full_v hold only the block-cyclic slice of rank seq_rank — token position p lives
+   * on rank (p / seq_block) % seq_world at local row (p / (seq_block*seq_world)) * seq_block + p % seq_block, so a
+   * slice is ordered by position and balanced at any length — while full_len keeps counting GLOBAL tokens (full_cap
+   * is the local capacity).  duo_rope_append then appends only the positions this rank owns; duo_attention_seq
+   * attends the local slice.  Streaming heads are not sharded.  The reference shards by head only
+   * (duo_attn/utils.py:151-179). */
+  int32_t seq_rank, seq_world, seq_block, seq_reserved;
 } duo_cache_state;
 
 typedef struct duo_layer duo_layer; /* opaque: desc + pre-encoded TMA descriptors (host memory) */
@@ -208,7 +216,7 @@ DUO_API int duo_add_rmsnorm(const void* x, const void* residual, const void* wei
 DUO_API int duo_silu_mul(const void* gate_up, void* out, int64_t rows, int32_t inter, int32_t dtype, void* stream);
 
 /*
- * EXPERIMENTAL building blocks of the sequence-sharded decode: a retrieval head's
+ * Building blocks of the sequence-sharded decode: a retrieval head's
  * cache is split by position over several layers / ranks; each slice is attended separately and the slices are
  * combined with the online-softmax merge (what flash_attn_func computes over the whole cache in one call,
  * duo_attn/patch/llama.py:393-399, is recovered exactly up to fp32 rounding).
@@ -224,11 +232,21 @@ DUO_API int duo_silu_mul(const void* gate_up, void* out, int64_t rows, int32_t i
 DUO_API int duo_attention_partial(const duo_layer* layer, int64_t n_keys, const void* q, int64_t q_row_stride,
                                   float* out_o, float* out_lse, int32_t q_len, float scale, void* workspace,
                                   size_t workspace_bytes, void* stream);
+/*
+ * duo_attention_seq: one decode-sized chunk (group * q_len <= 16) of the sequence-sharded layout described at
+ * duo_cache_state.  Retrieval q-heads attend the local slice (token t sees the local rows of positions
+ * <= full_len + t) and report out_o / out_lse exactly as duo_attention_partial does; streaming q-heads (replicated on
+ * every rank) are computed normally into `out` ([batch][q_len][n_q][128], rows of retrieval heads untouched).
+ * Follow with duo_seq_merge, which exchanges the partials between the ranks and writes the retrieval rows of `out`.
+ */
+DUO_API int duo_attention_seq(const duo_layer* layer, const duo_cache_state* st, const void* q, int64_t q_row_stride,
+                              void* out, float* out_o, float* out_lse, int32_t q_len, float scale, void* workspace,
+                              size_t workspace_bytes, void* stream);
 DUO_API int duo_merge_partials(const float* o_parts, const float* lse_parts, int32_t n_parts, int64_t tokens,
                                int32_t heads_total, int32_t heads_used, void* out, int32_t dtype, void* stream);
 
 /*
- * EXPERIMENTAL (head-parallel TP): the per-layer exchange step of the reference's
+ * Head-parallel TP: the per-layer exchange step of the reference's
  * tensor-parallel sharding (duo_attn/utils.py:174-176, "sum" of the row-parallel o_proj / down_proj partials) as a
  * one-shot all-reduce over NVLink peer memory, fused with the residual add + RMSNorm that consumes it:
  *   out_res  = T( T(sum over ranks of partial) + residual )         (residual may be NULL: no add)
@@ -258,6 +276,31 @@ DUO_API void duo_comm_destroy(duo_comm* comm);
 DUO_API int duo_allreduce_add_rmsnorm(const duo_comm* comm, const void* partial, const void* residual,
                                       const void* weight, void* out_norm, void* out_res, int32_t rows, float eps,
                                       void* stream);
+
+/*
+ * duo_seq_merge: the exchange step of the sequence-sharded decode — one kernel that pushes this rank's (O, lse) partial
+ * rows into every rank's receive slots over NVLink peer memory (same push / release-flag / acquire-wait protocol and
+ * buffer ownership rules as duo_allreduce_add_rmsnorm), then merges the `world` partials of every row in rank order
+ * (bit-identical on all ranks) with the online-softmax rule of duo_merge_partials and writes
+ * out[tok][h][:] for h < heads_used in the activation dtype.  tokens * heads_used <= max_rows.
+ *   part_o fp32 [tokens][heads_total][128], part_lse fp32 [tokens][heads_total] (as written by duo_attention_seq)
+ *   data[r]: duo_seqcomm_data_bytes() bytes, flags[r]: duo_seqcomm_flag_bytes() bytes, zero-initialised, mapped on every
+ *   rank; local_state: device int32[max_rows + 1] zero-initialised (epochs; last word = peer-timeout error flag).
+ */
+typedef struct duo_seqcomm duo_seqcomm;
+typedef struct duo_seqcomm_desc {
+  void* data[8];
+  void* flags[8];
+  void* local_state;
+  int32_t rank, world;  /* 2 <= world <= 8 */
+  int32_t max_rows;     /* <= 512 */
+} duo_seqcomm_desc;
+DUO_API size_t duo_seqcomm_data_bytes(int32_t world, int32_t max_rows);
+DUO_API size_t duo_seqcomm_flag_bytes(int32_t world, int32_t max_rows);
+DUO_API int duo_seqcomm_create(const duo_seqcomm_desc* desc, duo_seqcomm** out);
+DUO_API void duo_seqcomm_destroy(duo_seqcomm* comm);
+DUO_API int duo_seq_merge(const duo_seqcomm* comm, const float* part_o, const float* part_lse, void* out, int32_t tokens,
+                          int32_t heads_total, int32_t heads_used, int32_t dtype, void* stream);
 
 DUO_API const char* duo_last_error_string(void);
 DUO_API int duo_version(void);

@@ -5,14 +5,19 @@ IS FlashAttention-2, and FA2 itself does not meet that bar element-for-element a
 restatement: P is rounded to bf16 block by block against the *running* max, so a few elements land up to a couple
 of bf16 ulps away (measured on the B200 box with the installed flash_attn 2.8.3 vs oracle.flash_attn_contract:
 0 violations for ordinary logits, 2.7e-4 of the elements — max |err| 0.0156 — when the softmax is sharp; see
-DESIGN.md §Parity).  The gate is therefore expressed RELATIVE TO THE REFERENCE'S OWN KERNEL wherever that kernel can run on
-the test's inputs (`assert_parity(..., fa2=...)`): the number of our elements outside rtol=1e-2 / atol=1e-3 may exceed
-FlashAttention-2's own count against the same oracle output by at most max(0.1 % of the elements, 2 elements — the
-granularity of a 512-element decode output), and we may have no element outside rtol=2e-2 / atol=8e-3 (two bf16
-ulps of an O(1) output) that FA2 does not have.  Where FA2 cannot produce the comparison (INT4 caches — the
-reference dequantises first —, kernel-family-vs-kernel-family checks) the absolute gate applies: at least 99.5 % of
-the elements inside the tolerance (2 elements for tiny outputs) and none outside the hard bound.  Every call appends
-the achieved counts to gpurun_out/parity_log.jsonl (summarised in profiles/r2_parity.md).  That the kernels are not
+DESIGN.md §Parity).  The gate therefore has two parts:
+
+  * absolute, against the oracle: at least 99.5 % of the elements within rtol=1e-2 / atol=1e-3 (rounded up to whole
+    elements: 3 of a 512-element decode output) and none outside rtol=2e-2 / atol=8e-3 (two bf16 ulps of an O(1) output);
+  * relative to the reference's own kernel, wherever it can run on the test's inputs (`fa2=` + `truth=`): against
+    EXACT fp64 attention on the same inputs, the number of our elements outside rtol=1e-2 / atol=1e-3 may exceed
+    FlashAttention-2's own count by at most max(0.1 % of the elements, 2), and we may have no hard-bound violation
+    that FA2 does not have.  (Measured against the oracle instead, FA2 looks better than it is: the oracle rounds P
+    against the same running max FA2 uses, so their rounding errors are correlated; a kernel with a different — equally
+    valid — reference for P, like the lazy reference of the tcgen05 kernel, is only comparable against exact math.
+    The log keeps both counts.)
+
+Every call appends the achieved counts to gpurun_out/parity_log.jsonl (summarised in profiles/r2_parity.md).  That the kernels are not
 LESS accurate than the reference's kernel is also asserted against an fp64 ground truth
 (tests/test_gpu_oracle_pin.py::test_accuracy_vs_fp64_truth_not_worse_than_flash_attn, tests/test_gpu_bench_shapes.py).
 """
@@ -46,35 +51,42 @@ def _counts(x, ref):
     return err, int(viol.sum().item()), int(hard.sum().item())
 
 
-def assert_parity(got: torch.Tensor, ref: torch.Tensor, what: str = "", fa2: torch.Tensor = None):
+def assert_parity(got: torch.Tensor, ref: torch.Tensor, what: str = "", fa2: torch.Tensor = None,
+                  truth: torch.Tensor = None):
     """``got`` (the CUDA product) against ``ref`` (oracle / reference output) at the north_star tolerance.
 
-    ``fa2``: output of the reference's own attention kernel (installed flash_attn_func) on the SAME inputs, when the
-    test can produce it.  The gate is then relative: our violation count may exceed FlashAttention-2's own count
-    against the same ``ref`` by at most max(1e-3 of the elements, 2 elements), and we may have no hard-bound
-    violation that FA2 does not have.  Without ``fa2`` (INT4 caches, GPU-vs-GPU comparisons) the absolute gate of the
-    header applies.  Every call logs what was achieved (``record``)."""
+    Absolute gate (always): at least 99.5 % of the elements of ``got`` within rtol/atol of ``ref`` and none outside the
+    hard bound.  Relative gate (when the test supplies ``fa2`` = the installed flash_attn_func's output and ``truth`` =
+    exact fp64 attention on the SAME inputs): measured against exact math, our count of elements outside rtol/atol may
+    exceed FlashAttention-2's own count by at most max(0.1 % of the elements, 2 elements), and we may have no
+    hard-bound violation FA2 does not have.  Every call logs what was achieved (``record``)."""
     got, ref = got.float(), ref.float()
     assert got.shape == ref.shape, (got.shape, ref.shape)
     assert torch.isfinite(got).all(), f"{what}: non-finite output"
     n = got.numel()
     err, n_viol, n_hard = _counts(got, ref)
     frac = n_viol / n
+    allowed = max(math.ceil(MAX_VIOLATION_FRACTION * n), 2)
+    log = dict(what=what, n=n, viol=n_viol, hard=n_hard, max_err=err.max().item())
+    rel_fail = ""
     if fa2 is not None:
         fa2 = fa2.float().to(ref.device)
         e2, fa2_viol, fa2_hard = _counts(fa2, ref)
-        allowed, hard_allowed = fa2_viol + max(math.ceil(1e-3 * n), 2), fa2_hard
-        rule = f"FlashAttention-2's own {fa2_viol} + eps"
-        record("parity", what=what, n=n, viol=n_viol, hard=n_hard, max_err=err.max().item(), fa2_viol=fa2_viol,
-               fa2_hard=fa2_hard, fa2_max_err=e2.max().item())
-    else:
-        allowed, hard_allowed = max(math.ceil(MAX_VIOLATION_FRACTION * n), 2), 0
-        rule = f"{MAX_VIOLATION_FRACTION:.0e} of the elements"
-        record("parity", what=what, n=n, viol=n_viol, hard=n_hard, max_err=err.max().item())
-    if n_viol > allowed or n_hard > hard_allowed:
+        log.update(fa2_viol=fa2_viol, fa2_hard=fa2_hard, fa2_max_err=e2.max().item())
+        if truth is not None:
+            truth = truth.float().to(ref.device)
+            _, t_ours, th_ours = _counts(got, truth)
+            _, t_fa2, th_fa2 = _counts(fa2, truth)
+            log.update(truth_viol=t_ours, truth_hard=th_ours, fa2_truth_viol=t_fa2, fa2_truth_hard=th_fa2)
+            eps = max(math.ceil(1e-3 * n), 2)
+            if t_ours > t_fa2 + eps or th_ours > th_fa2:
+                rel_fail = (f"; against exact math {t_ours} elements outside the tolerance vs FlashAttention-2's "
+                            f"{t_fa2} (+{eps} allowed), hard bound {th_ours} vs {th_fa2}")
+    record("parity", **log)
+    if n_viol > allowed or n_hard > 0 or rel_fail:
         idx = tuple(int(i) for i in torch.nonzero(err == err.max())[0])
         raise AssertionError(
-            f"{what}: {n_viol} of {n} elements ({frac:.2e}) outside rtol={RTOL}/atol={ATOL} (allowed {allowed}: {rule}), "
-            f"{n_hard} outside the hard bound (allowed {hard_allowed}); max |err| {err.max().item():.5f} at {idx} "
-            f"(got {got[idx].item():.5f}, ref {ref[idx].item():.5f})")
+            f"{what}: {n_viol} of {n} elements ({frac:.2e}) outside rtol={RTOL}/atol={ATOL} (allowed {allowed}), "
+            f"{n_hard} outside the hard bound; max |err| {err.max().item():.5f} at {idx} "
+            f"(got {got[idx].item():.5f}, ref {ref[idx].item():.5f}){rel_fail}")
     return err.max().item(), frac

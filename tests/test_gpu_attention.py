@@ -39,29 +39,52 @@ class Fa2Shadow:
         self.n_full, self.G, self.sink, self.recent = n_full, groups, sink, recent
         self.kv = None
 
+    @staticmethod
+    def exact(q, k, v):
+        """fp64 bottom-right-causal GQA attention on the GPU (row-blocked): no rounding anywhere."""
+        B, Sq, Hq, Dh = q.shape
+        Sk, Hkv = k.shape[1], k.shape[2]
+        G = Hq // Hkv
+        out = torch.empty(B, Sq, Hq, Dh, dtype=torch.float64, device=q.device)
+        kd, vd = k.double(), v.double()
+        jj = torch.arange(Sk, device=q.device)[None, :]
+        for r0 in range(0, Sq, 512):
+            r1 = min(Sq, r0 + 512)
+            ii = torch.arange(r0, r1, device=q.device)[:, None] + (Sk - Sq)
+            for h in range(Hq):
+                s = torch.einsum("bqd,bkd->bqk", q[:, r0:r1, h].double(), kd[:, :, h // G]) / Dh ** 0.5
+                s = s.masked_fill((jj > ii)[None], float("-inf"))
+                out[:, r0:r1, h] = torch.einsum("bqk,bkd->bqd", torch.softmax(s, -1), vd[:, :, h // G])
+        return out
+
     def step(self, q, k, v):
+        """-> (flash_attn_func output, exact fp64 output) of this chunk, both fp32 on the CPU."""
         if self.fa is None:
-            return None
+            return None, None
         nf, G = self.n_full, self.G
         q, k, v = q.cuda(), k.cuda(), v.cuda()
         if self.kv is None:
             out = self.fa(q, k, v, causal=True)
+            truth = self.exact(q, k, v)
             fk, fv, sk, sv = k[:, :, :nf], v[:, :, :nf], k[:, :, nf:], v[:, :, nf:]
         else:
             fk, fv, sk, sv = self.kv
             fk, fv = torch.cat([fk, k[:, :, :nf]], 1), torch.cat([fv, v[:, :, :nf]], 1)
             sk, sv = torch.cat([sk, k[:, :, nf:]], 1), torch.cat([sv, v[:, :, nf:]], 1)
-            parts = []
+            parts, tparts = [], []
             if nf > 0:
                 parts.append(self.fa(q[:, :, : nf * G], fk, fv, causal=True))
+                tparts.append(self.exact(q[:, :, : nf * G], fk, fv))
             if nf * G < q.shape[2]:
                 parts.append(self.fa(q[:, :, nf * G :], sk, sv, causal=True))
+                tparts.append(self.exact(q[:, :, nf * G :], sk, sv))
             out = torch.cat(parts, dim=2)
+            truth = torch.cat(tparts, dim=2)
         if sk.shape[1] > self.sink + self.recent:
             sk = torch.cat([sk[:, : self.sink], sk[:, sk.shape[1] - self.recent :]], 1)
             sv = torch.cat([sv[:, : self.sink], sv[:, sv.shape[1] - self.recent :]], 1)
         self.kv = (fk, fv, sk, sv)
-        return out.float().cpu()
+        return out.float().cpu(), truth.float().cpu()
 
     def evict(self, n):
         if self.kv is not None:
@@ -89,7 +112,8 @@ def run_schedule(Hq, Hkv, n_full, sink, recent, chunks, B=1, dtype=torch.bfloat1
         got = out.float().cpu()
         outs.append(got)
         if check:
-            assert_parity(got, ref, f"chunk {i} (len {S}, past {cache.kv_seq_len - S})", fa2=shadow.step(q, k, v))
+            fa2, truth = shadow.step(q, k, v)
+            assert_parity(got, ref, f"chunk {i} (len {S}, past {cache.kv_seq_len - S})", fa2=fa2, truth=truth)
         worst = max(worst, (got - ref.float()).abs().max().item())
         ev = (evict_after or {}).get(i, 0)
         if ev:

@@ -205,7 +205,7 @@ def test_graph_step_raises_when_the_cache_is_full():
     gates = np.array([[1.0, 0.0], [0.0, 1.0]])
     enable_llama_duo_attention_static_kv_cache_eval(model, gates)
     model.cuda()
-    cache = DuoAttentionStaticKVCache(model, gates, 1, 40, 4, 6)
+    cache = DuoAttentionStaticKVCache(model, gates, 1, 40, 4, 6, prefilling_chunk_size=37)
     ids = torch.randint(0, 512, (1, 37)).cuda()
     with torch.no_grad():
         model(input_ids=ids, past_key_values=cache, use_cache=True)
@@ -216,5 +216,6 @@ def test_graph_step_raises_when_the_cache_is_full():
         assert cache.kv_seq_len == 40
         with pytest.raises(ValueError, match="Trying to put 1 KVs into a cache with max size 40"):
             graph.step(tok)
-        with pytest.raises(ValueError, match="captured in a DuoDecodeGraph"):
-            model(input_ids=torch.zeros(1, 100, dtype=torch.long).cuda(), past_key_values=cache, use_cache=True)
+        cache.clear()
+        with pytest.raises(ValueError, match="captured in a DuoDecodeGraph"):  # 39 tokens > staging capacity 37
+            model(input_ids=torch.zeros(1, 39, dtype=torch.long).cuda(), past_key_values=cache, use_cache=True)

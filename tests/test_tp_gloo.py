@@ -86,3 +86,41 @@ def test_sharded_layers_sum_to_the_single_process_result():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _reshard_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from duo_attention_b200.seqshard import SeqShardPlan
+
+        torch.manual_seed(0)  # same "global" cache on every rank
+        mask = np.array([[1.0, 0.0, 1.0, 1.0], [0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0]])
+        n_tok, cap, block, B, Dm = 77, 96, 8, 2, 4
+        plan = tp.plan_heads(mask, world)
+        sp = SeqShardPlan(world, block)
+        ok = True
+        for l in range(mask.shape[0]):
+            glob = torch.randn(B, 4, cap, Dm)                      # [B, original head id, position, d]
+            mine = [h for h in plan.owners[l][rank] if mask[l][h] > 0.5]
+            src = glob[:, mine].contiguous() if mine else torch.zeros(B, 0, cap, Dm)
+            full_ids = [h for h in range(4) if mask[l][h] > 0.5]
+            dst = torch.zeros(B, len(full_ids), sp.capacity(cap) + 1, Dm)
+            tp.reshard_heads_to_seq(src, plan.owners[l], mask[l], rank, world, n_tok, block, dst)
+            pos = sp.positions(rank, n_tok)
+            want = glob[:, full_ids][:, :, pos] if full_ids else dst[:, :, : len(pos)]
+            ok = ok and torch.equal(dst[:, :, : len(pos)], want) and bool((dst[:, :, len(pos):] == 0).all())
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reshard_from_head_parallel_to_sequence_sharded_layout():
+    """tp.reshard_heads_to_seq (point-to-point, what DuoSeqShardKVCache.load_from_head_parallel runs per layer):
+    every rank ends up with its block-cyclic position slice of EVERY retrieval head, in reordered head order."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_reshard_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
