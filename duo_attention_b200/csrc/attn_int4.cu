@@ -583,6 +583,22 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
 // the row-major kernel.  The fragment algebra is also checked lane-by-lane on the CPU
 // (tests/test_int4_swapab_layout.py).
 // =============================================================================================
+// Debug build only (`make trace`, -DDUO_TRACE): per-CTA %globaltimer stamps (start, main loop done, partial published,
+// exit) into a caller-provided buffer — profiles/int4_trace.py turns them into a launch timeline.
+#ifdef DUO_TRACE
+__device__ unsigned long long* g_duo_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(int slot) {
+  if (threadIdx.x == 0 && g_duo_trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_duo_trace[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 4 + slot] = t;
+  }
+}
+#define DUO_TRACE_STAMP(slot) trace_stamp(slot)
+#else
+#define DUO_TRACE_STAMP(slot)
+#endif
+
 constexpr int D8_TILE = 128;
 constexpr int D8_STAGES = 3;
 constexpr int D8_PACK = D8_TILE * 64;
@@ -603,6 +619,7 @@ __device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
 }
 
 __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const I4Params pin) {
+  DUO_TRACE_STAMP(0);
   I4Params p = pin;
   if (pin.dstate) {
     p.full_len = pin.dstate[0];
@@ -919,6 +936,7 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     }
   }
   cp_async_wait<0>();
+  DUO_TRACE_STAMP(1);
 
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
@@ -1009,6 +1027,7 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     s_is_last = (prev == p.splits_full - 1);
   }
   __syncthreads();
+  DUO_TRACE_STAMP(2);
   if (!s_is_last) return;
   __threadfence();
   const float* po = p.ws_o + item * p.splits_full * (long long)(D8_ROWS * 128);
@@ -1051,6 +1070,7 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     store_row_elem(r, d, a0f * inv, a1f * inv);
   }
   if (tid == 0) p.counters[item] = 0;
+  DUO_TRACE_STAMP(3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1231,6 +1251,12 @@ static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const v
   DUO_CUDA_TRY(cudaGetLastError());
   return DUO_OK;
 }
+
+#ifdef DUO_TRACE
+extern "C" __attribute__((visibility("default"))) int duo_debug_set_trace(void* buf) {
+  return cudaMemcpyToSymbol(g_duo_trace, &buf, sizeof(void*)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int launch_attn_int4(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
                      int q_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {

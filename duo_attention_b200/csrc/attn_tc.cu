@@ -10,7 +10,8 @@
 //               2-stage rings with separate full/empty mbarriers for K and V
 //   warp 1      MMA issuer (one thread): S_i = Q_i K^T (SS) and O_i += P_i V (TS, P read from TMEM),
 //               order S0 S1 | PV0 S0' PV1 S1' | ... so the tensor pipe works on tile 1-i while
-//               softmax warpgroup i is busy (ping-pong); completion signalled with tcgen05.commit
+//               softmax warpgroup i is busy (ping-pong); PV_i is issued in two 64-key halves, the first as soon as
+//               P for keys 0-63 is published; completion signalled with tcgen05.commit
 //   warp 2      TMEM allocator (512 columns: S0 | S1 | O0 | O1; P_i aliases the first 64 columns of S_i)
 //   warps 4-7   softmax warpgroup 0: one thread per query row of tile 0 — tcgen05.ld S row, mask,
 //   warps 8-11  softmax warpgroup 1   online softmax with a LAZY reference (O in TMEM is rescaled only when a row max
@@ -140,7 +141,7 @@ struct TcType<__half> {
 struct TcBarriers {
   uint64_t q_full;
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[2], p_full[2], o_done[2];
+  uint64_t s_full[2], p_lo[2], p_hi[2], o_lo[2], o_done[2];
   uint32_t tmem_base;
 };
 
@@ -215,7 +216,9 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_init(&bars.v_full[s], 1);
       mbar_init(&bars.v_empty[s], 1);
       mbar_init(&bars.s_full[s], 1);
-      mbar_init(&bars.p_full[s], 128);
+      mbar_init(&bars.p_lo[s], 128);
+      mbar_init(&bars.p_hi[s], 128);
+      mbar_init(&bars.o_lo[s], 1);
       mbar_init(&bars.o_done[s], 1);
     }
     fence_barrier_init();
@@ -273,14 +276,27 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                   kk > 0);
         }
       };
-      auto issue_pv = [&](int slot, int j) {
+      // O_slot += P V for one 64-key half of tile j (4 MMAs of 16 keys): the first half is issued as soon as the softmax
+      // warpgroup has published P for keys 0-63, i.e. while it is still computing the exponentials of keys 64-127
+      auto issue_pv_half = [&](int slot, int j, int half) {
         const int st = j & 1;
         const uint32_t va = v_addr + st * TC_TILE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int kk = half * 4 + k4;
           umma_ts(tmem + 256 + slot * 128, tmem + slot * 128 + kk * 8,
                   make_smem_desc(va + kk * 2048, TC_BOX_BYTES, 1024), idesc_pv, (j > 0 || kk > 0));
         }
+      };
+      auto issue_pv = [&](int slot, int j) {
+        mbar_wait(&bars.p_lo[slot], j & 1);
+        tc_fence_after();
+        issue_pv_half(slot, j, 0);
+        umma_commit(&bars.o_lo[slot]);  // only waited for on a mis-speculated second half (softmax warps)
+        mbar_wait(&bars.p_hi[slot], j & 1);
+        tc_fence_after();
+        issue_pv_half(slot, j, 1);
+        umma_commit(&bars.o_done[slot]);
       };
       mbar_wait(&bars.q_full, 0);
       mbar_wait(&bars.k_full[0], 0);
@@ -300,19 +316,13 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (more) mbar_wait(&bars.k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
         mbar_wait(&bars.v_full[st], ph);
         // ---- tile 0: PV0(j) then S0(j+1)
-        mbar_wait(&bars.p_full[0], j & 1);
-        tc_fence_after();
         issue_pv(0, j);
-        umma_commit(&bars.o_done[0]);
         if (more) {
           issue_s(0, j + 1);
           umma_commit(&bars.s_full[0]);
         }
         // ---- tile 1: PV1(j) then S1(j+1)
-        mbar_wait(&bars.p_full[1], j & 1);
-        tc_fence_after();
         issue_pv(1, j);
-        umma_commit(&bars.o_done[1]);
         umma_commit(&bars.v_empty[st]);
         if (more) {
           issue_s(1, j + 1);
@@ -353,11 +363,11 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       // as large as 2^8 (lazy reference, exact in the final O/l); a mis-speculation (rare after the first tile)
       // falls through to the generic path below, which recomputes from the still intact S.
       if (!need_mask && __all_sync(0xffffffffu, m_ref != -INFINITY)) {
-        const float mref_c = m_ref * c;
-        uint32_t pk[64];
+        float mref_c = m_ref * c;
+        uint32_t pk[32];
         uint32_t ra[32], rb[32];
         float mx = -INFINITY, rs = 0.f;
-        auto consume = [&](const uint32_t (&r)[32], int ch) {
+        auto consume = [&](const uint32_t (&r)[32], int q) {  // 32 logits -> 16 packed P words pk[16 q ...]
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
@@ -365,7 +375,7 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             const float p0 = fast_exp2(v0 * c - mref_c);
             const float p1 = fast_exp2(v1 * c - mref_c);
             rs += p0 + p1;
-            pk[ch * 16 + i] = TcType<T>::pack(p0, p1);
+            pk[q * 16 + i] = TcType<T>::pack(p0, p1);
           }
         };
         tmem_ld32(tS, ra);
@@ -375,27 +385,59 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tmem_wait_ld();
         tmem_ld32(tS + 64, ra);
         consume(rb, 1);
-        tmem_wait_ld();
-        tmem_ld32(tS + 96, rb);
-        consume(ra, 2);
-        tmem_wait_ld();
-        consume(rb, 3);
-        const bool outgrown = (mx - m_ref) * c > 8.0f;
-        if (!__any_sync(0xffffffffu, outgrown)) {
-          uint32_t half0[32], half1[32];
+        // ---- keys 0-63 done.  If none of their logits outgrew the reference, publish P_lo now: the issuer starts
+        // PV for these keys while this warpgroup still works on keys 64-127.
+        if (!__any_sync(0xffffffffu, (mx - m_ref) * c > 8.0f)) {
+          tmem_st32(tS, pk);  // overwrites S columns 0-31 (keys 0-31, already in registers / consumed)
+          l_run += rs;
+          tmem_wait_st();     // (also completes the load of columns 64-95 into ra)
+          tc_fence_before();
+          mbar_arrive(&bars.p_lo[slot]);
+          tmem_wait_ld();
+          tmem_ld32(tS + 96, rb);
+          mx = -INFINITY;
+          rs = 0.f;
+          consume(ra, 0);
+          tmem_wait_ld();
+          consume(rb, 1);
+          const bool outgrown = (mx - m_ref) * c > 8.0f;
+          if (__any_sync(0xffffffffu, outgrown)) {
+            // Rare: a key of the second half outgrew the reference after P_lo was handed over.  Everything accumulated
+            // so far — O including the PV_lo product of this tile, l including the first half's row sum — is relative
+            // to the old reference: scale it by alpha once PV_lo has executed, then redo the second half from S
+            // (columns 64-127 are intact: P_lo went to columns 0-31, P_hi will go to 32-63).
+            float alpha = 1.0f;
+            if (outgrown) {
+              alpha = fast_exp2((m_ref - mx) * c);
+              m_ref = mx;
+              mref_c = m_ref * c;
+              l_run *= alpha;
+            }
+            mbar_wait_spin(&bars.o_lo[slot], j & 1);
+            tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            half0[i] = pk[i];
-            half1[i] = pk[32 + i];
+            for (int ch = 0; ch < 4; ++ch) {
+              tmem_ld32(tO + ch * 32, ra);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ra[i] = __float_as_uint(__uint_as_float(ra[i]) * alpha);
+              tmem_st32(tO + ch * 32, ra);
+            }
+            tmem_ld32(tS + 64, ra);
+            tmem_ld32(tS + 96, rb);
+            tmem_wait_ld();
+            rs = 0.f;
+            consume(ra, 0);
+            consume(rb, 1);
           }
-          tmem_st32(tS, half0);
-          tmem_st32(tS + 32, half1);
+          tmem_st32(tS + 32, pk);
           l_run += rs;
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&bars.p_full[slot]);  // (one arrival per warp instead of per thread measured no faster)
+          mbar_arrive(&bars.p_hi[slot]);
           continue;
         }
+        tmem_wait_ld();  // retire the in-flight load before the generic path reuses the TMEM load unit state
       }
       // ---- generic path: masked tiles, first tile, mis-speculated tiles -----------------------------------
       float sv[128];
@@ -460,7 +502,8 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       l_run += rs;
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars.p_full[slot]);
+      mbar_arrive(&bars.p_lo[slot]);
+      mbar_arrive(&bars.p_hi[slot]);
     }
 
     // ---- epilogue: O / l -> global ----------------------------------------------------------------
