@@ -9,8 +9,11 @@ Workload (BASELINE.json configs[1] + the metric's 1M-context decode point):
                 every step, the reference's benchmark_static.py:96-103 protocol)  -> `value` (tokens/s)
     * prefill : 131,072 tokens in chunks of 32,768 through the same patched model        -> `prefill` object
 
-One process per GPU (`torchrun` for N > 1): KV heads are sharded across ranks (head-parallel TP, one NCCL
-all-reduce on the attention output and one on the MLP output per layer); total work is fixed -> "strong".
+One process per GPU (`torchrun` for N > 1).  Prefill: KV heads are sharded across ranks (head-parallel TP, the reference's
+rule: one all-reduce on the attention output and one on the MLP output per layer).  Decode: retrieval heads are
+SEQUENCE-sharded (every rank streams 1/N of every retrieval head; one peer-memory exchange of the (O, lse) partials per
+layer, fused one-shot all-reduce for the MLP), reached from the prefill layout by a timed reshard.  Total work is fixed
+-> "strong".
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ctx 1048576] [--prefill-ctx 131072]
 """
@@ -74,6 +77,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fa2", action="store_true", help="skip the same-box FlashAttention-2 micro-comparison")
     ap.add_argument("--no-graph", action="store_true", help="drive decode eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--head-tp-decode", action="store_true",
+                    help="N > 1: decode head-parallel like the reference's TP rule instead of sequence-sharded (A/B)")
     args = ap.parse_args()
     if args.pattern is None:
         args.pattern = ARCHS[args.arch][1]
@@ -185,7 +190,9 @@ def workload_config(args, sparsity):
                     f"{sparsity:.2f}, sink {SINK}/recent {RECENT}, batch 1: decode @ctx={args.ctx} "
                     f"(evict_last(1) per step) + prefill {args.prefill_ctx} tokens in chunks of {args.chunk}",
         "pattern": args.pattern, "kv_format": args.kv_format, "ctx": args.ctx, "prefill_ctx": args.prefill_ctx, "chunk": args.chunk, "layers": args.layers,
-        "parallelism": f"head-tp{args.gpus}",
+        "parallelism": (f"prefill head-tp{args.gpus}, decode sequence-sharded retrieval heads x{args.gpus} "
+                        f"(attention replicated, MLP tp{args.gpus})") if args.gpus > 1 and args.kv_format == "bf16"
+                       and not getattr(args, "head_tp_decode", False) else f"head-tp{args.gpus}",
         "l2": "inputs larger than L2: every decode step streams >2 GB of KV per layer (126 MB L2), "
               "prefill chunks stream the whole KV cache",
     }
@@ -240,9 +247,10 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def build_model(args, mask, rank, world, dev):
-    """Random-init Llama-3-8B (or this rank's head-parallel shard of it) directly on the GPU, patched through
-    the drop-in API."""
+def build_model(args, mask, rank, world, dev, seq_shard=False):
+    """Random-init Llama-3-8B (or this rank's shard of it) directly on the GPU, patched through the drop-in API.
+    ``seq_shard=False``: head-parallel shard (KV heads split over the ranks, the reference's TP rule);
+    ``seq_shard=True`` : decode-phase shard with sequence-sharded retrieval heads (attention replicated, MLP split)."""
     import torch
     from transformers import LlamaConfig, LlamaForCausalLM
     from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
@@ -254,27 +262,34 @@ def build_model(args, mask, rank, world, dev):
     cfgd.update(ARCHS[args.arch][0])
     cfgd["num_hidden_layers"] = args.layers
     plan = tp.plan_heads(mask[: args.layers], world)  # which (reordered) kv heads each rank owns, per layer
-    local_mask = plan.local_mask(rank)
-    cfgd["num_attention_heads"] = cfgd["num_attention_heads"] // world
-    cfgd["num_key_value_heads"] = cfgd["num_key_value_heads"] // world
+    if seq_shard:
+        local_mask = mask[: args.layers]
+    else:
+        local_mask = plan.local_mask(rank)
+        cfgd["num_attention_heads"] = cfgd["num_attention_heads"] // world
+        cfgd["num_key_value_heads"] = cfgd["num_key_value_heads"] // world
     cfgd["intermediate_size"] = cfgd["intermediate_size"] // world
     cfg = LlamaConfig(**cfgd, attn_implementation="eager")
     with torch.device("meta"):
         model = LlamaForCausalLM(cfg)
     model = model.to(torch.float16 if args.kv_format == "int4" else torch.bfloat16).to_empty(device=dev)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    g_rep = torch.Generator(device=dev).manual_seed(99)  # replicated tensors must be identical on every rank
     with torch.no_grad():
         for name, prm in model.named_parameters():
             if prm.dim() == 1:
                 prm.fill_(1.0)
             else:
-                prm.normal_(0.0, 0.02, generator=g)
+                split = ".mlp." in name or (".self_attn." in name and not seq_shard)
+                prm.normal_(0.0, 0.02, generator=g if split else g_rep)
     model.model.rotary_emb = LlamaRotaryEmbedding(config=cfg, device=dev)
     model.eval()
     enable_duo_attention_eval(model, local_mask, SINK, RECENT)
-    if world > 1:
+    if world > 1 and seq_shard:
+        tp.install_seq_shard(model)
+    elif world > 1:
         tp.install_allreduce(model)
-    return model, local_mask
+    return model, local_mask, plan
 
 
 def fill_cache_synthetic(cache, ctx):
@@ -320,7 +335,7 @@ def main():
     _C.load()  # fail loudly if the CUDA extension is missing
     mask, sparsity = head_pattern(args.pattern, args.sparsity)
     mask = mask[: args.layers]
-    model, local_mask = build_model(args, mask, rank, world, dev)
+    model, local_mask, head_plan = build_model(args, mask, rank, world, dev)
     vocab = {**L3_8B, **ARCHS[args.arch][0]}["vocab_size"]
 
     def barrier():
@@ -338,7 +353,8 @@ def main():
     result = {}
     launches = 0
     # ------------------------------------------------------------------ prefill @128K
-    cache = DuoAttentionStaticKVCache(model, local_mask, 1, args.ctx + 8, SINK, RECENT,
+    seq_decode = world > 1 and args.kv_format == "bf16" and not args.head_tp_decode
+    cache = DuoAttentionStaticKVCache(model, local_mask, 1, (args.prefill_ctx if seq_decode else args.ctx) + 8, SINK, RECENT,
                                       prefilling_chunk_size=args.chunk if not args.no_prefill else 64,
                                       kv_format="int4" if args.kv_format == "int4" else "same")
     gcpu = torch.Generator().manual_seed(1)
@@ -389,6 +405,27 @@ def main():
         }
 
     # ------------------------------------------------------------------ decode @1M
+    decode_mask = local_mask
+    if seq_decode:
+        # N > 1: the decode phase runs with SEQUENCE-SHARDED retrieval heads (tp.install_seq_shard): every rank streams
+        # 1/N of every retrieval head, attention weights and streaming heads replicated, MLP tensor-parallel.  The
+        # head-parallel caches the prefill just filled are moved over by point-to-point resharding (timed), then the
+        # cache is filled synthetically to the decode context like at N = 1.
+        from duo_attention_b200.kv_cache import DuoSeqShardKVCache
+
+        model_sp, decode_mask, _ = build_model(args, mask, rank, world, dev, seq_shard=True)
+        cache_sp = DuoSeqShardKVCache(model_sp, decode_mask, 1, args.ctx + 8, SINK, RECENT)
+        if not args.no_prefill:
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cache_sp.load_from_head_parallel(cache, head_plan)
+            e1.record()
+            barrier()
+            result["prefill"]["reshard_to_sequence_sharded_ms"] = max_over_ranks(e0.elapsed_time(e1))
+        del cache, model
+        torch.cuda.empty_cache()
+        model, cache = model_sp, cache_sp
     fill_cache_synthetic(cache, args.ctx)
     tok_dev = torch.randint(0, vocab, (1, 1), generator=gcpu).to(dev)
     tok_host = torch.randint(0, vocab, (1, 1), generator=gcpu).pin_memory()
@@ -468,7 +505,14 @@ def main():
 
     ms_step = ms_total / args.steps
     peaks = load_peaks()
-    by = decode_bytes_per_token(local_mask, args.ctx, 68 if args.kv_format == "int4" else 256)  # this rank's bytes
+    if seq_decode:  # this rank's slice of every retrieval head + all (replicated) streaming heads
+        from duo_attention_b200.seqshard import SeqShardPlan
+
+        n_loc = SeqShardPlan(world, model._duo_seq.block).local_len(rank, args.ctx + 1)
+        n_f = decode_mask.sum(1)
+        by = float(((n_f * n_loc + (decode_mask.shape[1] - n_f) * (SINK + RECENT + 1)) * 2 * 256).sum())
+    else:
+        by = decode_bytes_per_token(local_mask, args.ctx, 68 if args.kv_format == "int4" else 256)  # this rank's bytes
     attn_ms_max = max_over_ranks(attn_ms)
     achieved = by / (attn_ms / 1e3) / 1e9
     line = {

@@ -33,7 +33,7 @@ def _torchrun(script, world, port, marker, timeout=420, extra_env=None):
 
 
 def _worlds():
-    return [w for w in (2, 4, 8) if w <= N_GPUS] or [2]
+    return sorted({2, N_GPUS}) if N_GPUS >= 2 else [2]
 
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs")
