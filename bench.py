@@ -539,13 +539,27 @@ def main():
         "a100_published": {"decode_ms_per_tok_1M": 55.0, "note": "reference figure, 1xA100-80G, other hardware"},
     }
     line.update(result)
-    if world == 1 and args.kv_format == "bf16" and not args.no_fa2 and args.arch == "llama3-8b-1048k":
+    if world == 1 and args.kv_format == "bf16" and not args.no_fa2:
+        graph = None
         del cache
         torch.cuda.empty_cache()
-        try:
-            line["fa2_same_box"] = fa2_same_box(dev, args.ctx, args.chunk, args.prefill_ctx)
+        try:  # end to end: the reference's static forward + cache on its own libraries, same weights, same protocol
+            from baseline import fa2_restated
+
+            ref = fa2_restated.run(model, [int(x) for x in mask.sum(1)], SINK, RECENT, args.ctx, args.prefill_ctx,
+                                   args.chunk, vocab, do_prefill=not args.no_prefill)
+            ref["decode"]["ours_over_reference"] = line["e2e"]["value"] / ref["decode"]["value"]
+            if "prefill" in ref and "prefill" in line:
+                ref["prefill"]["ours_over_reference"] = line["prefill"]["value"] / ref["prefill"]["value"]
+            line["reference_gpu_same_box"] = ref
         except Exception as e:  # the comparison is informative, never fatal
-            line["fa2_same_box"] = {"error": repr(e)}
+            line["reference_gpu_same_box"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+        if args.arch == "llama3-8b-1048k":
+            try:
+                line["fa2_same_box"] = fa2_same_box(dev, args.ctx, args.chunk, args.prefill_ctx)
+            except Exception as e:
+                line["fa2_same_box"] = {"error": repr(e)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_sample(args.ctx, mask)
         line["cpu_baseline"] = {"value": cb["tok_s"], "unit": "tokens/s", "cores": cb["cores"], "kind": "port",

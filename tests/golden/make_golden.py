@@ -235,6 +235,37 @@ def make_int4_fixtures(O, GC):
                             checksum=np.float64(GC.int4_checksum(chunks)))
         print("wrote int4", case["name"], "tokens", sum(case["chunks"]), "final lens", lens[-1])
 
+    # ---- the demo's enable function (demo/w8a8kv4_llama.py:659-729), unmodified, on a stand-in fused-qkv model ----
+    Hq, Hkv, Dh, hid = 8, 4, 8, 24
+    g = torch.Generator().manual_seed(77)
+    gates = [[1.0, 0.0, 0.6, 0.2], [0.0, 0.0, 1.0, 1.0], [0.3, 0.9, 0.1, 0.7]]
+    layers, before = [], []
+    for _ in gates:
+        qkv = types.SimpleNamespace(
+            weight=types.SimpleNamespace(data=torch.randint(-128, 128, ((Hq + 2 * Hkv) * Dh, hid), generator=g,
+                                                            dtype=torch.int8)),
+            dequant_scale=torch.rand((Hq + 2 * Hkv) * Dh, generator=g).to(torch.float16))
+        o = types.SimpleNamespace(weight=types.SimpleNamespace(data=torch.randint(-128, 128, (hid, Hq * Dh), generator=g,
+                                                                                  dtype=torch.int8)))
+        before.append((qkv.weight.data.clone(), qkv.dequant_scale.clone(), o.weight.data.clone()))
+        attn = types.SimpleNamespace(qkv_proj=qkv, o_proj=o, q_size=Hq * Dh, kv_size=Hkv * Dh, num_heads=Hq,
+                                     num_kv_heads=Hkv, head_dim=Dh)
+        attn.register_buffer = lambda name, t, a=attn: setattr(a, name, t)
+        layers.append(types.SimpleNamespace(self_attn=attn))
+    holder = torch.nn.Linear(1, 1).to(torch.float16)
+    model = types.SimpleNamespace(parameters=lambda: holder.parameters(), model=types.SimpleNamespace(layers=layers))
+    ref_w8.enable_llama_duo_attention_eval(model, gates, 64, 256)
+    np.savez_compressed(
+        os.path.join(HERE, "w8a8kv4_enable.npz"), gates=np.array(gates),
+        **{f"qkv_w_in_{i}": b[0].numpy() for i, b in enumerate(before)},
+        **{f"qkv_s_in_{i}": b[1].numpy() for i, b in enumerate(before)},
+        **{f"o_w_in_{i}": b[2].numpy() for i, b in enumerate(before)},
+        **{f"qkv_w_{i}": l.self_attn.qkv_proj.weight.data.numpy() for i, l in enumerate(layers)},
+        **{f"qkv_s_{i}": l.self_attn.qkv_proj.dequant_scale.numpy() for i, l in enumerate(layers)},
+        **{f"o_w_{i}": l.self_attn.o_proj.weight.data.numpy() for i, l in enumerate(layers)},
+        **{f"heads_{i}": l.self_attn.full_attention_heads.float().numpy() for i, l in enumerate(layers)})
+    print("wrote w8a8kv4_enable (sink/recent attrs:", layers[0].self_attn.sink_size, layers[0].self_attn.recent_size, ")")
+
 
 def main():
     from oracle import duo_oracle as O

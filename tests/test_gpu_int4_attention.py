@@ -118,3 +118,30 @@ def test_int4_large_chunk_kernel_families_agree():
         outs.append(res)
     for a, b in zip(*outs):
         assert_parity(a, b, "INT4 chunk: tcgen05-on-fp16-image vs mma.sync fused-dequant kernel")
+
+
+def test_w8a8kv4_attention_core_through_the_fused_qkv_boundary():
+    """duo_w8a8kv4_attention (what demo/w8a8kv4_llama.py:174-287 does between the fused int8 projection and the output
+    quantisation): fp16 activation buffer [bsz*q_len, q+2kv] in, fp32 on-the-fly RoPE, INT4-KV cache, attention out —
+    vs the oracle's flashinfer-style RoPE + INT4 attention core."""
+    import types
+
+    from duo_attention_b200.patch import w8a8kv4
+
+    dev = torch.device("cuda:0")
+    Hq, Hkv, n_full, sink, recent, theta = 8, 2, 1, 8, 24, 10000.0
+    cache = DuoKVCache(1, Hq, Hkv, D, [n_full], 1, 512, sink, recent, torch.float16, dev, stage_cap=200,
+                       kv_format="int4")
+    mod = types.SimpleNamespace(layer_idx=0, head_dim=D, num_heads=Hq, num_kv_heads=Hkv, rope_theta=theta)
+    g = torch.Generator().manual_seed(31)
+    past, pos = None, 0
+    for S in [150, 1, 1, 20, 1, 130, 1]:
+        act = torch.randn(S, (Hq + 2 * Hkv) * D, generator=g).to(torch.float16)
+        out = w8a8kv4.duo_w8a8kv4_attention(mod, act.to(dev), cache, S)
+        q = act[:, : Hq * D].reshape(1, S, Hq, D)
+        k = act[:, Hq * D : (Hq + Hkv) * D].reshape(1, S, Hkv, D)
+        v = act[:, (Hq + Hkv) * D :].reshape(1, S, Hkv, D)
+        qr, kr = O.rope_flashinfer(q, k, pos, 1.0, theta)
+        ref, past = O.int4_attention_core(qr, kr, v, past, n_full, Hq // Hkv, sink, recent)
+        assert_parity(out.view(1, S, Hq, D).float().cpu(), ref.float(), f"chunk of {S} at {pos}")
+        pos += S
