@@ -32,16 +32,21 @@ def enable_duo_attention_eval(model, full_attention_heads, sink_size, recent_siz
         raise ValueError(f"Model type {model.config.model_type} not supported")
 
 
-def enable_llama_duo_attention_static_kv_cache_eval(model, full_attention_heads):
+def enable_llama_duo_attention_static_kv_cache_eval(model, full_attention_heads, rope: str = "hf"):
     """llama.py:557-598.  The caller builds a ``DuoAttentionStaticKVCache`` (which carries sink/recent)
     and passes it as ``past_key_values`` every call (benchmark_static.py:58-103).  Llama static eval
-    keeps bf16 logits (static_kv_cache.py:360-364)."""
-    _install(model, full_attention_heads, None, None, logits_float=False)
+    keeps bf16 logits (static_kv_cache.py:360-364).
+
+    ``rope`` (extra keyword): "hf" rotates with HuggingFace's tables in the activation dtype, bit-exact with the
+    tuple path (the parity target north_star names); "flashinfer" reproduces what the reference's static forward
+    actually calls (llama.py:347-352 -> flashinfer_utils.py:29-59): fp32 angles on the fly, one rounding, linear
+    ``rope_scaling["factor"]`` only."""
+    _install(model, full_attention_heads, None, None, logits_float=False, rope=rope)
 
 
-def enable_mistral_duo_attention_static_kv_cache_eval(model, full_attention_heads):
+def enable_mistral_duo_attention_static_kv_cache_eval(model, full_attention_heads, rope: str = "hf"):
     """mistral.py:557-598; mistral's static driver returns fp32 logits (static_kv_cache.py:612-617)."""
-    _install(model, full_attention_heads, None, None, logits_float=True)
+    _install(model, full_attention_heads, None, None, logits_float=True, rope=rope)
 
 
 __all__ = [

@@ -77,8 +77,9 @@ def _fusable(layer):
 
 
 def duo_attention_layer_forward(attn, hidden_states, cos, sin, kv_cache: DuoKVCache, layer_idx: int,
-                                rope_mode: int = _C.ROPE_HF):
-    """The hot path of one layer (replaces llama.py:146-306 / :309-434)."""
+                                rope_mode: int = _C.ROPE_HF, project: bool = True):
+    """The hot path of one layer (replaces llama.py:146-306 / :309-434).  ``project=False`` returns the attention
+    context ``[B, S, Hq * D]`` before ``o_proj`` (the pipelined tensor-parallel driver projects it block by block)."""
     plan = attn._duo_plan
     if plan.wqkv is None or plan.wqkv.device != hidden_states.device:
         _fuse_qkv(attn)
@@ -86,7 +87,57 @@ def duo_attention_layer_forward(attn, hidden_states, cos, sin, kv_cache: DuoKVCa
     qkv = torch.nn.functional.linear(hidden_states, plan.wqkv, plan.bqkv)
     out = torch.empty(B, S, plan.n_kv * plan.group, plan.head_dim, dtype=qkv.dtype, device=qkv.device)
     kv_cache.attend(layer_idx, qkv, cos, sin, rope_mode, out)
-    return attn.o_proj(out.view(B, S, -1))
+    return attn.o_proj(out.view(B, S, -1)) if project else out.view(B, S, -1)
+
+
+def _tp_layer_pipelined(layer, ctx, h, next_norm, group, n_blocks):
+    """Head-parallel TP, large chunks: the two bandwidth-bound all-reduces of a layer (attention output and MLP output,
+    duo_attn/utils.py:174-179 — 256 MiB each for a 32K-token chunk) overlapped with the GEMMs by row blocks.  Block b's
+    row-parallel o_proj partial is all-reduced (NCCL, asynchronously on the communicator's stream) while block b+1 is
+    projected; its add+RMSNorm -> gate|up -> SiLU*mul -> down runs while later blocks are still in flight, and the MLP
+    partials are reduced the same way.  Only the last block's exchange of each site is exposed.
+    ctx ``[1, S, Hq_local * D]``, h ``[1, S, hidden]`` (updated in place); returns the normalised input of the next
+    layer."""
+    import torch.distributed as dist
+
+    from .. import ops
+
+    S = ctx.shape[1]
+    step = (S + n_blocks - 1) // n_blocks
+    spans = [(r, min(S, r + step)) for r in range(0, S, step)]
+    ln2 = layer.post_attention_layernorm
+    parts, works = [], []
+    for r0, r1 in spans:
+        a = layer.self_attn.o_proj(ctx[:, r0:r1])
+        works.append(dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        parts.append(a)
+    mparts, mworks = [], []
+    for (r0, r1), a, w in zip(spans, parts, works):
+        w.wait()  # stream-level wait: the host keeps enqueueing
+        x, _ = ops.add_rmsnorm(a, h[:, r0:r1], ln2.weight, ln2.variance_epsilon)
+        m = _mlp_forward(layer.mlp, x)
+        mworks.append(dist.all_reduce(m, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        mparts.append(m)
+    outs = []
+    for (r0, r1), m, w in zip(spans, mparts, mworks):
+        w.wait()
+        x, _ = ops.add_rmsnorm(m, h[:, r0:r1], next_norm.weight, next_norm.variance_epsilon)
+        outs.append(x)
+    return torch.cat(outs, dim=1)
+
+
+def plans_head_dim(model):
+    return model.model.layers[0].self_attn._duo_plan.head_dim
+
+
+def _rope_theta_and_scale(cfg):
+    """(rope_theta, linear factor) the way the reference's static forward reads them (llama.py:347-350:
+    ``config.rope_scaling["factor"]`` if set, whatever the scaling type), across transformers config layouts."""
+    rp = getattr(cfg, "rope_parameters", None) or {}
+    rs = getattr(cfg, "rope_scaling", None) or {}
+    theta = getattr(cfg, "rope_theta", None) or rp.get("rope_theta") or 10000.0
+    factor = rs.get("factor") or rp.get("factor") or 1.0
+    return float(theta), float(factor)
 
 
 def _new_dynamic_cache(model, batch_size, first_len):
@@ -133,8 +184,18 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
         position_ids = torch.arange(past_len, past_len + S, dtype=torch.long, device=inputs_embeds.device)[None]
     else:
         position_ids = position_ids.view(-1, S).long()[:1]
-    cos, sin = base.rotary_emb(inputs_embeds, position_ids)  # [1, S, D] in the activation dtype
-    cos, sin = cos[0].contiguous(), sin[0].contiguous()
+    rope_mode = getattr(self, "_duo_rope_mode", _C.ROPE_HF)
+    if rope_mode == _C.ROPE_FP32:
+        # the reference's STATIC path rotates with flashinfer: fp32 angles computed on the fly from the first position
+        # of the chunk, linear `rope_scale` only (llama.py:347-352, flashinfer_utils.py:29-59)
+        theta, factor = _rope_theta_and_scale(self.config)
+        pos = position_ids[0].to(torch.float32) / factor
+        idx = torch.arange(plans_head_dim(self) // 2, dtype=torch.float32, device=pos.device)
+        ang = pos[:, None] * torch.pow(torch.tensor(theta, device=pos.device), -2.0 * idx / plans_head_dim(self))[None]
+        cos, sin = torch.cat([ang.cos(), ang.cos()], -1).contiguous(), torch.cat([ang.sin(), ang.sin()], -1).contiguous()
+    else:
+        cos, sin = base.rotary_emb(inputs_embeds, position_ids)  # [1, S, D] in the activation dtype
+        cos, sin = cos[0].contiguous(), sin[0].contiguous()
     h = inputs_embeds.contiguous() if input_ids is not None else inputs_embeds.clone()  # updated in place below
     tp_on = getattr(self, "_duo_tp", False)
     seq_on = getattr(self, "_duo_seq", None) is not None  # sequence-sharded decode: attention output needs no exchange
@@ -159,8 +220,15 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
             return ops.add_rmsnorm(part, res, w, eps)
 
         x, _ = ops.add_rmsnorm(h, None, layers[0].input_layernorm.weight, layers[0].input_layernorm.variance_epsilon)
+        pipe_rows = getattr(self, "_duo_tp_pipeline_rows", 4096)
+        pipelined = tp_on and not seq_on and comm is None and B == 1 and S >= pipe_rows
         for idx, layer in enumerate(layers):
-            a = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
+            if pipelined and idx + 1 < len(layers):
+                ctx = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx, rope_mode, project=False)
+                x = _tp_layer_pipelined(layer, ctx, h, layers[idx + 1].input_layernorm, self._duo_tp_group,
+                                        getattr(self, "_duo_tp_pipeline_blocks", 4))
+                continue
+            a = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx, rope_mode)
             ln2 = layer.post_attention_layernorm
             if seq_on:  # merged attention output is already complete (and bit-identical) on every rank
                 x, h = ops.add_rmsnorm(a, h, ln2.weight, ln2.variance_epsilon)
@@ -183,7 +251,7 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
         for idx, layer in enumerate(layers):
             res = h
             x = layer.input_layernorm(h)
-            x = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx)
+            x = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx, rope_mode)
             if tp_on and not seq_on:
                 x = all_reduce_sum(x, self._duo_tp_group)
             h = res + x
@@ -202,7 +270,7 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
     return CausalLMOutputWithPast(logits=logits, past_key_values=cache if use_cache is not False else None)
 
 
-def install(model, full_attention_heads, sink_size, recent_size, logits_float=True):
+def install(model, full_attention_heads, sink_size, recent_size, logits_float=True, rope="hf"):
     """Shared body of enable_{llama,mistral}_duo_attention_eval (llama.py:504-554): reorder weights so
     retrieval heads come first, remember the split, swap the model forward."""
     from .reorder import reorder_linear_weights, reorder_full_attn_heads
@@ -227,5 +295,8 @@ def install(model, full_attention_heads, sink_size, recent_size, logits_float=Tr
     model._duo_sink = sink_size
     model._duo_recent = recent_size
     model._duo_logits_float = logits_float
+    if rope not in ("hf", "flashinfer"):
+        raise ValueError(f"rope must be 'hf' or 'flashinfer', got {rope!r}")
+    model._duo_rope_mode = _C.ROPE_FP32 if rope == "flashinfer" else _C.ROPE_HF
     model.forward = types.MethodType(duo_causal_lm_forward, model)
     return model

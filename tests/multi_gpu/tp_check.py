@@ -34,8 +34,9 @@ def main():
     sink, recent = 4, 12
     shard, local_mask = tp.shard_model(full, gates, rank, world)
     enable_duo_attention_eval(shard, local_mask, sink, recent)
-    tp.install_allreduce(shard)
     shard.to(dev)
+    tp.install_allreduce(shard)
+    shard._duo_tp_pipeline_rows, shard._duo_tp_pipeline_blocks = 128, 3  # chunks of >= 128 rows: pipelined exchange
     single = copy.deepcopy(full)
     enable_duo_attention_eval(single, gates, sink, recent)
     single.to(dev)

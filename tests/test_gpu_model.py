@@ -219,3 +219,35 @@ def test_graph_step_raises_when_the_cache_is_full():
         cache.clear()
         with pytest.raises(ValueError, match="captured in a DuoDecodeGraph"):  # 39 tokens > staging capacity 37
             model(input_ids=torch.zeros(1, 39, dtype=torch.long).cuda(), past_key_values=cache, use_cache=True)
+
+
+@pytest.mark.parametrize("kind", ["llama", "mistral"])
+def test_static_path_with_flashinfer_rope_matches_reference_run_logits(kind):
+    """enable_*_static_kv_cache_eval(..., rope="flashinfer") against the logits the REFERENCE's static driver produced
+    (tests/golden/model_{llama,mistral}_static.npz: static_kv_cache.py:318-805 + flashinfer-style fp32 RoPE, run in fp32
+    by tests/golden/make_golden.py) — product (bf16, GPU) vs reference directly, without the oracle in between."""
+    import os
+
+    import golden_cases as GC
+    from duo_attn.patch import enable_mistral_duo_attention_static_kv_cache_eval
+
+    case = next(c for c in GC.MODEL_CASES if c["name"] == f"{kind}_static")
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", f"model_{kind}_static.npz"))
+    model, ids, _ = GC.make_tiny_model(case)
+    model = model.to(torch.bfloat16)
+    gates = np.array(case["gates"])
+    enable = (enable_llama_duo_attention_static_kv_cache_eval if kind == "llama"
+              else enable_mistral_duo_attention_static_kv_cache_eval)
+    enable(model, gates, rope="flashinfer")
+    model.cuda()
+    cache = DuoAttentionStaticKVCache(model, gates, 1, case["max_size"], case["sink"], case["recent"],
+                                      prefilling_chunk_size=max(case["chunks"]))
+    with torch.no_grad():
+        for i, x in enumerate(ids):
+            out = model(input_ids=x.cuda(), past_key_values=cache, use_cache=True)
+            torch.testing.assert_close(out.logits.float().cpu()[0, 0], torch.from_numpy(gold["logits"][0, i]),
+                                       rtol=5e-2, atol=5e-2)
+            ev = case.get("evict_after", {}).get(i, 0)
+            if ev:
+                cache.evict_last(ev)
+            assert cache.kv_seq_len == int(gold["lens"][i][0])
