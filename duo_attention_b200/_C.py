@@ -21,7 +21,7 @@ DECODE_MAX_Q = 16
 # every symbol include/duo_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
     "duo_layer_create", "duo_layer_destroy", "duo_workspace_bytes", "duo_rope_append", "duo_attention",
-    "duo_attention_mma", "duo_state_advance", "duo_state_set", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
+    "duo_attention_mma", "duo_decode_fused", "duo_state_advance", "duo_state_set", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
     "duo_attention_partial", "duo_merge_partials", "duo_attention_seq",
     "duo_seqcomm_data_bytes", "duo_seqcomm_flag_bytes", "duo_seqcomm_create", "duo_seqcomm_destroy", "duo_seq_merge",
     "duo_comm_data_bytes", "duo_comm_flag_bytes", "duo_comm_create", "duo_comm_destroy", "duo_allreduce_add_rmsnorm",
@@ -85,6 +85,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = [vp, C.POINTER(CacheState), vp, i64, vp, i32, f32, vp, sz, vp]
         fn.restype = C.c_int
+    lib.duo_decode_fused.argtypes = [vp, C.POINTER(CacheState), vp, i64, vp, vp, i32, vp, i32, f32, vp, sz, vp]
+    lib.duo_decode_fused.restype = C.c_int
     lib.duo_state_advance.argtypes = [vp, i32, i32, i32, vp]
     lib.duo_state_advance.restype = C.c_int
     lib.duo_state_set.argtypes = [vp, i64, i64, i64, vp]

@@ -61,6 +61,9 @@ int launch_attn_mma_partial(const duo_layer* L, long long n_keys, const void* q,
 int launch_attn_mma_seq(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride, void* out,
                         float* part_o, float* part_lse, int q_len, float scale, void* workspace, size_t workspace_bytes,
                         cudaStream_t stream);
+int launch_decode_fused(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
+                        const void* cos, const void* sin, int rope_mode, void* out, int q_len, float scale,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_merge_partials(const float* o_parts, const float* lse_parts, int n_parts, long long tokens, int heads_total,
                           int heads_used, void* out, int dtype, cudaStream_t stream);
 int launch_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res,
@@ -277,6 +280,32 @@ int duo_attention(const duo_layer* layer, const duo_cache_state* st, const void*
     return launch_attn_tc(layer, st, q, q_row_stride, out, q_len, scale, (cudaStream_t)stream);
   return launch_attn_mma(layer, st, q, q_row_stride, out, q_len, scale, workspace, workspace_bytes,
                          (cudaStream_t)stream);
+}
+
+int duo_decode_fused(const duo_layer* layer, const duo_cache_state* st, const void* qkv, int64_t qkv_row_stride,
+                     const void* cos, const void* sin, int32_t rope_mode, void* out, int32_t q_len, float scale,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_chunk(layer, st, q_len, "duo_decode_fused");
+  if (rc) return rc;
+  if (!qkv || !out || (rope_mode != DUO_ROPE_NONE && (!cos || !sin))) {
+    set_error("duo_decode_fused: null buffer");
+    return DUO_EINVAL;
+  }
+  if (rope_mode < DUO_ROPE_NONE || rope_mode > DUO_ROPE_FP32) {
+    set_error("duo_decode_fused: bad rope_mode %d", rope_mode);
+    return DUO_EINVAL;
+  }
+  if (layer->d.kv_format != DUO_KV_SAME || layer->d.group * q_len > 16 || st->seq_world != 0) {
+    set_error("duo_decode_fused: 16-bit unsharded caches and group * q_len <= 16 only (got group %d, q_len %d)",
+              layer->d.group, q_len);
+    return DUO_EINVAL;
+  }
+  if (qkv_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(qkv) & 15)) {
+    set_error("duo_decode_fused: qkv rows must be 16-byte aligned (row stride a multiple of 8 elements)");
+    return DUO_EINVAL;
+  }
+  return launch_decode_fused(layer, st, qkv, qkv_row_stride, cos, sin, rope_mode, out, q_len, scale, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
 }
 
 // test / tuning hook: force the mma.sync kernel family even for shapes the tcgen05 kernel takes

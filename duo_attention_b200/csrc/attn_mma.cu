@@ -57,7 +57,44 @@ struct AttnParams {
   float* part_lse;
   int no_causal;
   int seq_rank, seq_world, seq_block;
+  // FUSED decode step (duo_decode_fused): `q` points at the RAW fused qkv rows; the kernel rotates q in registers,
+  // builds the K/V tile of the new tokens in shared memory (K rotated), appends those rows to the caches (retrieval:
+  // rows full_len + t; streaming: sink / ring slots, i.e. the ring commit) and attends them — no rope_append /
+  // stream_commit launches and no staging round trip.
+  const void* cos;
+  const void* sin;
+  int rope_mode;
+  long long k_off, v_off;  // element offsets of the k / v sections inside a qkv row
+  void *full_k, *full_v, *ring_k, *ring_v;
+  long long full_cap;
+  int ring_slots;
 };
+
+// RoPE of 8 consecutive head_dim elements d .. d+7 (d < 64) and their partners d+64 .. d+71, arithmetic of
+// rope_append_kernel (kv_ops.cu): HF mode rounds every product and the sum to T, fp32 mode rounds once.
+template <typename T>
+__device__ __forceinline__ void rope8(uint4& lo, uint4& hi, const void* cos, const void* sin, int mode, int tok, int d) {
+  T* xl = reinterpret_cast<T*>(&lo);
+  T* xh = reinterpret_cast<T*>(&hi);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float a = RopeCvt<T>::to_f(xl[e]), bb = RopeCvt<T>::to_f(xh[e]);
+    float ol, oh;
+    if (mode == DUO_ROPE_HF) {
+      const T* ct = reinterpret_cast<const T*>(cos) + (long long)tok * kHeadDim;
+      const T* st = reinterpret_cast<const T*>(sin) + (long long)tok * kHeadDim;
+      ol = rope_hf<T>(a, -bb, RopeCvt<T>::to_f(ct[d + e]), RopeCvt<T>::to_f(st[d + e]));
+      oh = rope_hf<T>(bb, a, RopeCvt<T>::to_f(ct[d + 64 + e]), RopeCvt<T>::to_f(st[d + 64 + e]));
+    } else {
+      const float* ct = reinterpret_cast<const float*>(cos) + (long long)tok * kHeadDim;
+      const float* st = reinterpret_cast<const float*>(sin) + (long long)tok * kHeadDim;
+      ol = rope_f32(a, -bb, ct[d + e], st[d + e]);
+      oh = rope_f32(bb, a, ct[d + 64 + e], st[d + 64 + e]);
+    }
+    xl[e] = RopeCvt<T>::from_f(ol);
+    xh[e] = RopeCvt<T>::from_f(oh);
+  }
+}
 
 // rows of the block-cyclic slice of `rank` that hold positions < n  (host twin: seqshard.SeqShardPlan.local_len)
 __host__ __device__ __forceinline__ long long seq_local_len(long long n, int rank, int world, int block) {
@@ -68,7 +105,33 @@ __host__ __device__ __forceinline__ long long seq_local_len(long long n, int ran
   return full_rounds * block + extra;
 }
 
-template <typename T, int KEY_WARPS>
+// same for two packed elements (d, d+1) and their partners (d+64, d+65): the Q fragments of the decode kernel
+template <typename T>
+__device__ __forceinline__ void rope2(uint32_t& lo2, uint32_t& hi2, const void* cos, const void* sin, int mode, int tok,
+                                      int d) {
+  T* xl = reinterpret_cast<T*>(&lo2);
+  T* xh = reinterpret_cast<T*>(&hi2);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float a = RopeCvt<T>::to_f(xl[e]), bb = RopeCvt<T>::to_f(xh[e]);
+    float ol, oh;
+    if (mode == DUO_ROPE_HF) {
+      const T* ct = reinterpret_cast<const T*>(cos) + (long long)tok * kHeadDim;
+      const T* st = reinterpret_cast<const T*>(sin) + (long long)tok * kHeadDim;
+      ol = rope_hf<T>(a, -bb, RopeCvt<T>::to_f(ct[d + e]), RopeCvt<T>::to_f(st[d + e]));
+      oh = rope_hf<T>(bb, a, RopeCvt<T>::to_f(ct[d + 64 + e]), RopeCvt<T>::to_f(st[d + 64 + e]));
+    } else {
+      const float* ct = reinterpret_cast<const float*>(cos) + (long long)tok * kHeadDim;
+      const float* st = reinterpret_cast<const float*>(sin) + (long long)tok * kHeadDim;
+      ol = rope_f32(a, -bb, ct[d + e], st[d + e]);
+      oh = rope_f32(bb, a, ct[d + 64 + e], st[d + 64 + e]);
+    }
+    xl[e] = RopeCvt<T>::from_f(ol);
+    xh[e] = RopeCvt<T>::from_f(oh);
+  }
+}
+
+template <typename T, int KEY_WARPS, bool FUSED>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
 duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_constant__ CUtensorMap map_fv,
                     const __grid_constant__ CUtensorMap map_rk, const __grid_constant__ CUtensorMap map_rv,
@@ -78,8 +141,9 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     p.full_len = pin.dstate[0];
     p.total = pin.dstate[1];
     p.lo = pin.dstate[2];
-    const long long nk = p.seq_world > 1 ? seq_local_len(p.full_len + p.q_len, p.seq_rank, p.seq_world, p.seq_block)
-                                         : p.full_len + p.q_len;
+    const long long nk = FUSED ? p.full_len
+                         : p.seq_world > 1 ? seq_local_len(p.full_len + p.q_len, p.seq_rank, p.seq_world, p.seq_block)
+                                           : p.full_len + p.q_len;
     long long kps = (nk + p.splits_full - 1) / p.splits_full;
     kps = (kps + TILE - 1) / TILE * TILE;
     p.keys_per_split = (int)(kps < TILE ? TILE : kps);
@@ -134,20 +198,29 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     if (p.seq_world > 1) return seq_local_len(p.full_len + t + 1, p.seq_rank, p.seq_world, p.seq_block);
     return p.full_len + t + 1;
   };
+  // FUSED: the new tokens' K/V are not in the caches yet; they form one extra tile built in shared memory, processed
+  // after the TMA tiles by the CTA that owns the end of the key range (streaming heads: their only CTA)
+  bool has_new = false;
+  long long new_base = 0;  // key index of the first new token in this CTA's key index space
   if (is_full) {
-    const long long nkeys = vis_count(tok_max);
+    const long long nkeys = FUSED ? p.full_len : vis_count(tok_max);
     a0 = (long long)split * p.keys_per_split;
     a1 = min(nkeys, a0 + (long long)p.keys_per_split);
     if (a1 < a0) a1 = a0;
+    has_new = FUSED && (split == p.splits_full - 1);
+    new_base = p.full_len;
   } else {
     a0 = 0;
     a1 = p.cache_scan;
     b0 = p.W;
-    b1 = (long long)p.W + tok_max + 1;
+    b1 = FUSED ? b0 : (long long)p.W + tok_max + 1;
+    has_new = FUSED;
+    new_base = p.W;
   }
   const int nA = (int)((a1 - a0 + TILE - 1) / TILE);
   const int nB = (int)((b1 - b0 + TILE - 1) / TILE);
-  const int n_tiles = nA + nB;
+  const int n_tiles = nA + nB;                       // tiles fetched by TMA
+  const int n_iter = n_tiles + (has_new ? 1 : 0);    // + the tile of the new tokens
   const CUtensorMap* mk = is_full ? &map_fk : &map_rk;
   const CUtensorMap* mv = is_full ? &map_fv : &map_rv;
   const int head_coord = is_full ? (b * p.n_full + kvh) : (b * p.n_stream + (kvh - p.n_full));
@@ -200,6 +273,18 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
         qa[kk][hf] = v0;
         qa[kk][hf + 2] = v1;
       }
+      if constexpr (FUSED) {
+        if (ok && p.rope_mode != DUO_ROPE_NONE) {  // partner of head_dim d is d + 64: k-step kk pairs with kk + 4
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int d = kk * 16 + half * 8 + 2 * t4;
+              rope2<T>(qa[kk][hf + 2 * half], qa[kk + 4][hf + 2 * half], p.cos, p.sin, p.rope_mode, tok, d);
+            }
+          }
+        }
+      }
     }
   }
 
@@ -216,15 +301,65 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
   const int lrow = lane & 7;
   const int lmat = lane >> 3;  // 0..3
 
-  for (int i = 0; i < n_tiles; ++i) {
+  for (int i = 0; i < n_iter; ++i) {
     __syncthreads();  // everyone is done with tile i-1 -> its stage may be refilled
-    if (tid == 0 && i + STAGES - 1 < n_tiles) issue(i + STAGES - 1);
-    const int s = i % STAGES;
-    mbar_wait(&full_bar[s], (i / STAGES) & 1);
-    const uint32_t sK = smem_u32(smem + s * STAGE_BYTES);
+    uint32_t sK;
+    long long j0, jend;
+    if (!FUSED || i < n_tiles) {
+      if (tid == 0 && i + STAGES - 1 < n_tiles) issue(i + STAGES - 1);
+      const int s = i % STAGES;
+      mbar_wait(&full_bar[s], (i / STAGES) & 1);
+      sK = smem_u32(smem + s * STAGE_BYTES);
+      j0 = tile_start(i);
+      jend = (i < nA) ? a1 : b1;
+    } else {
+      // ---- the new tokens: RoPE(K), append to the caches, build their K/V tile in stage 0 (every TMA tile has been
+      // consumed: all stages are free, and for streaming heads the ring has been read, so its slots may be rewritten)
+      uint8_t* st0 = smem;
+      for (int x = tid; x < STAGE_BYTES / 16; x += ATTN_THREADS) reinterpret_cast<uint4*>(st0)[x] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      const T* rows = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_batch_stride;
+      // destination row of new token r in the cache, or -1 if it is not kept (streaming: neither sink nor recent)
+      auto dst_row = [&](int r) -> long long {
+        if (is_full) return ((long long)b * p.n_full + kvh) * p.full_cap + p.full_len + r;
+        const long long pos = p.total + r;
+        long long slot;
+        if (pos < p.sink) slot = pos;
+        else if (r >= p.q_len - p.recent) slot = p.sink + (pos - p.sink) % p.recent;
+        else return -1;
+        return ((long long)b * p.n_stream + (kvh - p.n_full)) * p.ring_slots + slot;
+      };
+      T* gk = reinterpret_cast<T*>(is_full ? p.full_k : p.ring_k);
+      T* gv = reinterpret_cast<T*>(is_full ? p.full_v : p.ring_v);
+      for (int w = tid; w < p.q_len * 8; w += ATTN_THREADS) {  // K: (row, 8-element chunk c < 8 and its partner c + 8)
+        const int r = w >> 3, c = w & 7;
+        const T* src = rows + (long long)r * p.q_tok_stride + p.k_off + (long long)kvh * kHeadDim;
+        uint4 lo = *reinterpret_cast<const uint4*>(src + c * 8);
+        uint4 hi = *reinterpret_cast<const uint4*>(src + 64 + c * 8);
+        if (p.rope_mode != DUO_ROPE_NONE) rope8<T>(lo, hi, p.cos, p.sin, p.rope_mode, r, c * 8);
+        const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(st0 + off) = lo;
+        *reinterpret_cast<uint4*>(st0 + KV_BOX_BYTES + off) = hi;
+        const long long dr = dst_row(r);
+        if (dr >= 0) {
+          *reinterpret_cast<uint4*>(gk + dr * kHeadDim + c * 8) = lo;
+          *reinterpret_cast<uint4*>(gk + dr * kHeadDim + 64 + c * 8) = hi;
+        }
+      }
+      for (int w = tid; w < p.q_len * 16; w += ATTN_THREADS) {  // V: plain copy
+        const int r = w >> 4, c = w & 15;
+        const T* src = rows + (long long)r * p.q_tok_stride + p.v_off + (long long)kvh * kHeadDim;
+        const uint4 v = *reinterpret_cast<const uint4*>(src + c * 8);
+        *reinterpret_cast<uint4*>(st0 + (2 + (c >> 3)) * KV_BOX_BYTES + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
+        const long long dr = dst_row(r);
+        if (dr >= 0) *reinterpret_cast<uint4*>(gv + dr * kHeadDim + c * 8) = v;
+      }
+      __syncthreads();
+      sK = smem_u32(st0);
+      j0 = new_base;
+      jend = new_base + p.q_len;
+    }
     const uint32_t sV = sK + 2 * KV_BOX_BYTES;
-    const long long j0 = tile_start(i);
-    const long long jend = (i < nA) ? a1 : b1;
 
     // ---- S = Q K^T ------------------------------------------------------------------------------
     float sc[NT][4];
@@ -276,7 +411,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
       // reference a single-block kernel (FA2 / the oracle) uses; with only a few dozen keys the independent
       // per-warp references would otherwise be the largest source of bf16 rounding noise.  Long contexts
       // average that noise out and skip the extra barrier.
-      if (n_tiles <= 8) {
+      if (n_iter <= 8) {
         if (t4 == 0) {
           s_wmax[i & 1][warp][g] = mx[0];
           s_wmax[i & 1][warp][g + 8] = mx[1];
@@ -523,11 +658,17 @@ struct PartialMode {      // how the retrieval heads report (see AttnParams)
   float* part_lse = nullptr;
   bool no_causal = false;  // duo_attention_partial: plain slice, streaming heads not launched
 };
+struct FusedArgs {        // duo_decode_fused: q points at the raw qkv rows
+  const void* cos = nullptr;
+  const void* sin = nullptr;
+  int rope_mode = DUO_ROPE_NONE;
+};
+int stage_offset(const duo_layer_desc& d);  // api.cu
 
-template <typename T, int KEY_WARPS>
+template <typename T, int KEY_WARPS, bool FUSED = false>
 static int launch_variant(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride,
                           void* out, int q_len, float scale, void* workspace, size_t workspace_bytes,
-                          cudaStream_t stream, PartialMode pm = PartialMode()) {
+                          cudaStream_t stream, PartialMode pm = PartialMode(), FusedArgs fa = FusedArgs()) {
   const duo_layer_desc& d = L->d;
   constexpr int ROWS = 16 * (4 / KEY_WARPS);
   AttnParams p{};
@@ -565,9 +706,22 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   p.seq_rank = st->seq_rank;
   p.seq_world = st->seq_world;
   p.seq_block = st->seq_block;
-  const long long nkeys = partial ? st->full_len
+  const long long nkeys = (partial || FUSED) ? st->full_len
                           : st->seq_world > 1 ? seq_local_len(st->full_len + q_len, st->seq_rank, st->seq_world, st->seq_block)
                                               : st->full_len + q_len;
+  if (FUSED) {
+    p.cos = fa.cos;
+    p.sin = fa.sin;
+    p.rope_mode = fa.rope_mode;
+    p.k_off = (long long)n_q * kHeadDim;
+    p.v_off = (long long)(n_q + d.n_full + d.n_stream) * kHeadDim;
+    p.full_k = d.full_k;
+    p.full_v = d.full_v;
+    p.ring_k = d.ring_k;
+    p.ring_v = d.ring_v;
+    p.full_cap = d.full_cap;
+    p.ring_slots = stage_offset(d) + d.stage_cap;
+  }
   int splits = 1;
   if (d.n_full > 0) {
     const int budget = 2 * sm_count;
@@ -606,7 +760,7 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
 
   const int grid_x = d.n_full * p.n_rb * splits + (partial ? 0 : d.n_stream * p.n_rb);
   if (grid_x == 0) return DUO_OK;
-  auto kern = duo_attn_mma_kernel<T, KEY_WARPS>;
+  auto kern = duo_attn_mma_kernel<T, KEY_WARPS, FUSED>;
   static unsigned long long attr_mask = 0;  // per template instantiation, one bit per device
   if (int rc = ensure_dyn_smem(kern, ATTN_SMEM_BYTES, &attr_mask)) return rc;
   // a layer without retrieval (or without streaming) heads still needs *some* valid descriptor object in
@@ -695,6 +849,22 @@ int launch_attn_mma_partial(const duo_layer* L, long long n_keys, const void* q,
                                             stream, pm);
   return launch_variant<__half, 4>(L, &st, q, q_row_stride, nullptr, q_len, scale, workspace, workspace_bytes, stream,
                                    pm);
+}
+
+// One decode-sized chunk, everything in one launch (duo_decode_fused): RoPE(q, k) + KV append + mixed-head attention +
+// ring commit.  `qkv` is the raw fused projection output; it is NOT modified.
+int launch_decode_fused(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
+                        const void* cos, const void* sin, int rope_mode, void* out, int q_len, float scale,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  FusedArgs fa;
+  fa.cos = cos;
+  fa.sin = sin;
+  fa.rope_mode = rope_mode;
+  if (L->d.dtype == DUO_DT_BF16)
+    return launch_variant<__nv_bfloat16, 4, true>(L, st, qkv, row_stride, out, q_len, scale, workspace, workspace_bytes,
+                                                  stream, PartialMode(), fa);
+  return launch_variant<__half, 4, true>(L, st, qkv, row_stride, out, q_len, scale, workspace, workspace_bytes, stream,
+                                         PartialMode(), fa);
 }
 
 // Sequence-sharded decode step (duo_attention_seq): retrieval heads attend this rank's slice and report (O, lse)

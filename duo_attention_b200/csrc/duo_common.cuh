@@ -165,6 +165,34 @@ struct MmaOp<__half> {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// RoPE element arithmetic, shared by rope_append_kernel (kv_ops.cu) and the fused decode kernel (attn_mma.cu) so that
+// both produce the same bits.  `rot` is the rotate_half partner with its sign (exact in T).
+//   HF  : T(T(x*cos) + T(rot*sin))   — transformers' apply_rotary_pos_emb on T tensors (llama.py:177-184)
+//   fp32: T(x*cos + rot*sin), fp32 tables, one rounding (flashinfer semantics, flashinfer_utils.py:29-59)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct RopeCvt;
+template <>
+struct RopeCvt<__nv_bfloat16> {
+  __device__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <>
+struct RopeCvt<__half> {
+  __device__ static float to_f(__half v) { return __half2float(v); }
+  __device__ static __half from_f(float v) { return __float2half_rn(v); }
+};
+template <typename T>
+__device__ __forceinline__ float rope_hf(float x, float rot, float c, float s) {
+  const float a = RopeCvt<T>::to_f(RopeCvt<T>::from_f(__fmul_rn(x, c)));
+  const float r = RopeCvt<T>::to_f(RopeCvt<T>::from_f(__fmul_rn(rot, s)));
+  return __fadd_rn(a, r);  // the caller's conversion to T is the third rounding
+}
+__device__ __forceinline__ float rope_f32(float x, float rot, float c, float s) {
+  return __fmaf_rn(rot, s, __fmul_rn(x, c));
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

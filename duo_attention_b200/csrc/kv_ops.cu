@@ -119,11 +119,9 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const RopeAppendParams
       const Vec4<T> cv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(p.cos) + (long long)t * kHeadDim + lane * 4);
       const Vec4<T> sv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(p.sin) + (long long)t * kHeadDim + lane * 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const T a = Cvt<T>::from_f(__fmul_rn(Cvt<T>::to_f(xv.v[i]), Cvt<T>::to_f(cv.v[i])));
-        const T r = Cvt<T>::from_f(__fmul_rn(Cvt<T>::to_f(pv.v[i]), Cvt<T>::to_f(sv.v[i])));
-        xv.v[i] = Cvt<T>::from_f(__fadd_rn(Cvt<T>::to_f(a), Cvt<T>::to_f(r)));
-      }
+      for (int i = 0; i < 4; ++i)
+        xv.v[i] = Cvt<T>::from_f(rope_hf<T>(Cvt<T>::to_f(xv.v[i]), Cvt<T>::to_f(pv.v[i]), Cvt<T>::to_f(cv.v[i]),
+                                            Cvt<T>::to_f(sv.v[i])));
     } else {
       const float4 cv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.cos) + (long long)t * kHeadDim + lane * 4);
       const float4 sv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.sin) + (long long)t * kHeadDim + lane * 4);
@@ -131,7 +129,7 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const RopeAppendParams
       const float s[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        xv.v[i] = Cvt<T>::from_f(Cvt<T>::to_f(xv.v[i]) * c[i] + Cvt<T>::to_f(pv.v[i]) * s[i]);
+        xv.v[i] = Cvt<T>::from_f(rope_f32(Cvt<T>::to_f(xv.v[i]), Cvt<T>::to_f(pv.v[i]), c[i], s[i]));
     }
   }
 #pragma unroll

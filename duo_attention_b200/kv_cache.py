@@ -406,6 +406,21 @@ class DuoKVCache:
             scale = self.head_dim ** -0.5
         cp = cos.data_ptr() if cos is not None else None
         sp = sin.data_ptr() if sin is not None else None
+        if (self.kv_format == "same" and S * self.num_kv_groups <= _C.DECODE_MAX_Q and not force_mma
+                and qkv.stride(1) % 8 == 0 and qkv.data_ptr() % 16 == 0):
+            # decode-sized chunk: RoPE + append + attention + ring commit in ONE launch (q is not written back)
+            if self.profile_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _C.check(lib.duo_decode_fused(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode & 0xFF,
+                                          out.data_ptr(), S, float(scale), self.workspace.data_ptr(),
+                                          self.workspace.numel(), stream))
+            if self.profile_events is not None:
+                e1.record()
+                self.profile_events.append((e0, e1))
+            self.launch_count += 1
+            self.advance(l, S)
+            return out
         _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode, S, stream))
         ah, ast = h, st
         if self.kv_format == "int4" and st.full_len == 0 and st.total == 0:

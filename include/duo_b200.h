@@ -177,6 +177,19 @@ DUO_API int duo_attention(const duo_layer* layer, const duo_cache_state* st, con
                   void* out, int32_t q_len, float scale, void* workspace, size_t workspace_bytes,
                   void* stream);
 
+/*
+ * One launch for a whole decode-sized chunk (group * q_len <= 16, 16-bit caches): duo_rope_append + duo_attention +
+ * duo_stream_commit fused — RoPE of q in registers, RoPE(k) / v of the new tokens written straight to their final
+ * cache rows (retrieval: full_len + t; streaming: sink / ring slot, no staging round trip) and attended from a tile
+ * built in shared memory.  Replaces, per decoder layer and decode step, what the reference does in
+ * duo_attn/patch/llama.py:347-362 (RoPE), :353-362 + static_kv_cache.py:109-125 (append), :364-421 (attention) and
+ * :423-425 + static_kv_cache.py:127-167 (streaming compaction).  `qkv` as for duo_rope_append but NOT modified;
+ * cos / sin / rope_mode as for duo_rope_append (no DUO_ROPE_SKIP_Q); rows must be 16-byte aligned.
+ */
+DUO_API int duo_decode_fused(const duo_layer* layer, const duo_cache_state* st, const void* qkv, int64_t qkv_row_stride,
+                             const void* cos, const void* sin, int32_t rope_mode, void* out, int32_t q_len, float scale,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Diagnostic twin of duo_attention that always takes the mma.sync (bandwidth) kernel family, also for
  * chunk shapes duo_attention hands to the tcgen05 prefill kernel.  16-bit KV only.  Used by the parity
  * tests to cross-check the two kernel families against each other. */
