@@ -50,9 +50,7 @@ struct I4Params {
   long long full_cap, ring_slots;
   float scale_log2;
   int splits_full, keys_per_split, n_rb, cache_scan;
-  float* ws_o;
-  float* ws_ml;
-  int* counters;
+  SplitWs ws;  // split-KV partials + arrival counters (duo_common.cuh)
   const uint8_t *full_k, *full_v, *ring_k, *ring_v;
   const __half *fks, *fkz, *fvs, *fvz, *rks, *rkz, *rvs, *rvz;
 };
@@ -501,68 +499,18 @@ __global__ void __launch_bounds__(I4_THREADS, 2) duo_attn_int4_kernel(const I4Pa
     }
     return;
   }
-  // ---- split-KV publish + last-CTA merge (identical protocol to attn_mma.cu) ----------------------
+  // ---- split-KV publish + hierarchical merge (protocol of attn_mma.cu: split_kv_finish) ---------------------------
   const long long item = ((long long)b * p.n_full + kvh) * p.n_rb + rb;
-  float* wo = p.ws_o + (item * p.splits_full + split) * (long long)(ROWS * 128);
-  float* wml = p.ws_ml + (item * p.splits_full + split) * (long long)(ROWS * 2);
+  float* wo = p.ws.ws_o + (item * p.splits_full + split) * (long long)(ROWS * 128);
+  float* wml = p.ws.ws_ml + (item * p.splits_full + split) * (long long)(ROWS * 2);
   for (int idx = tid; idx < rows_here * 32; idx += I4_THREADS) {
     const int r = idx >> 5, d4 = (idx & 31) * 4;
     *reinterpret_cast<float4*>(&wo[r * 128 + d4]) = *reinterpret_cast<const float4*>(&sm_o[r * 128 + d4]);
   }
   if (tid < rows_here * 2) wml[tid] = sm_ml[tid];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int prev = atomicAdd(&p.counters[item], 1);
-    s_is_last = (prev == p.splits_full - 1);
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  const float* po = p.ws_o + item * p.splits_full * (long long)(ROWS * 128);
-  const float* pml = p.ws_ml + item * p.splits_full * (long long)(ROWS * 2);
-  float* cm_o = reinterpret_cast<float*>(smem);
-  float* cm_ml = reinterpret_cast<float*>(smem + 80 * 1024);
-  for (int rg = 0; rg < rows_here; rg += 16) {
-    const int rg_n = min(16, rows_here - rg);
-    for (int rr0 = 0; rr0 < rg_n; rr0 += 4) {  // four rows per pass: 16 loads in flight (split_merge_rows4)
-      const int nr = min(4, rg_n - rr0);
-      float4 acc4[4];
-      float mm4[4], ll4[4];
-      split_merge_rows4<ROWS>(po, pml, p.splits_full, warp, lane, rg + rr0, nr, acc4, mm4, ll4);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q < nr) {
-          *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr0 + q) * 128 + lane * 4]) = acc4[q];
-          if (lane == 0) {
-            cm_ml[(warp * 16 + rr0 + q) * 2] = mm4[q];
-            cm_ml[(warp * 16 + rr0 + q) * 2 + 1] = ll4[q];
-          }
-        }
-      }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < rg_n * 64; idx += I4_THREADS) {
-      const int rr = idx >> 6, d = (idx & 63) * 2;
-      float mm = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, cm_ml[(w * 16 + rr) * 2]);
-      float a0f = 0.f, a1f = 0.f, ll = 0.f;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const float mw = cm_ml[(w * 16 + rr) * 2];
-        if (mw == -INFINITY) continue;
-        const float f = fast_exp2(mw - mm);
-        a0f += f * cm_o[(w * 16 + rr) * 128 + d];
-        a1f += f * cm_o[(w * 16 + rr) * 128 + d + 1];
-        ll += f * cm_ml[(w * 16 + rr) * 2 + 1];
-      }
-      const float inv = ll > 0.f ? 1.f / ll : 0.f;
-      store_row_elem(rg + rr, d, a0f * inv, a1f * inv);
-    }
-    __syncthreads();
-  }
-  if (tid == 0) p.counters[item] = 0;
+  split_kv_finish<ROWS>(p.ws, item, split, p.splits_full, rows_here, reinterpret_cast<float*>(smem),
+                        reinterpret_cast<float*>(smem + 80 * 1024), &s_is_last,
+                        [&](int r, int d, float v0, float v1, float, float) { store_row_elem(r, d, v0, v1); });
 }
 
 // =============================================================================================
@@ -1011,65 +959,20 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     }
     return;
   }
-  // ---- split-KV publish + last-CTA merge (protocol of attn_mma.cu, 8 rows per item) --------------------------
+  // ---- split-KV publish + hierarchical merge (protocol of attn_mma.cu, 8 rows per item) -----------------------------
   const long long item = (long long)b * p.n_full + kvh;
-  float* wo = p.ws_o + (item * p.splits_full + split) * (long long)(D8_ROWS * 128);
-  float* wml = p.ws_ml + (item * p.splits_full + split) * (long long)(D8_ROWS * 2);
+  float* wo = p.ws.ws_o + (item * p.splits_full + split) * (long long)(D8_ROWS * 128);
+  float* wml = p.ws.ws_ml + (item * p.splits_full + split) * (long long)(D8_ROWS * 2);
   for (int idx = tid; idx < rows_total * 32; idx += I4_THREADS) {
     const int r = idx >> 5, d4 = (idx & 31) * 4;
     *reinterpret_cast<float4*>(&wo[r * 128 + d4]) = *reinterpret_cast<const float4*>(&sm_o[r * 128 + d4]);
   }
   if (tid < rows_total * 2) wml[tid] = sm_ml[tid];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int prev = atomicAdd(&p.counters[item], 1);
-    s_is_last = (prev == p.splits_full - 1);
-  }
-  __syncthreads();
   DUO_TRACE_STAMP(2);
-  if (!s_is_last) return;
-  __threadfence();
-  const float* po = p.ws_o + item * p.splits_full * (long long)(D8_ROWS * 128);
-  const float* pml = p.ws_ml + item * p.splits_full * (long long)(D8_ROWS * 2);
-  float* cm_o = w_o;    // [4 warps][8 rows][128]
-  float* cm_ml = w_ml;  // [4 warps][8 rows][2]
-  for (int r0 = 0; r0 < rows_total; r0 += 4) {  // four rows per pass: 16 loads in flight (split_merge_rows4)
-    const int nr = min(4, rows_total - r0);
-    float4 acc4[4];
-    float mm4[4], ll4[4];
-    split_merge_rows4<D8_ROWS>(po, pml, p.splits_full, warp, lane, r0, nr, acc4, mm4, ll4);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (q < nr) {
-        *reinterpret_cast<float4*>(&cm_o[(warp * D8_ROWS + r0 + q) * 128 + lane * 4]) = acc4[q];
-        if (lane == 0) {
-          cm_ml[(warp * D8_ROWS + r0 + q) * 2] = mm4[q];
-          cm_ml[(warp * D8_ROWS + r0 + q) * 2 + 1] = ll4[q];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < rows_total * 64; idx += I4_THREADS) {
-    const int r = idx >> 6, d = (idx & 63) * 2;
-    float mm = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) mm = fmaxf(mm, cm_ml[(w * D8_ROWS + r) * 2]);
-    float a0f = 0.f, a1f = 0.f, ll = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float mw = cm_ml[(w * D8_ROWS + r) * 2];
-      if (mw == -INFINITY) continue;
-      const float f = fast_exp2(mw - mm);
-      a0f += f * cm_o[(w * D8_ROWS + r) * 128 + d];
-      a1f += f * cm_o[(w * D8_ROWS + r) * 128 + d + 1];
-      ll += f * cm_ml[(w * D8_ROWS + r) * 2 + 1];
-    }
-    const float inv = ll > 0.f ? 1.f / ll : 0.f;
-    store_row_elem(r, d, a0f * inv, a1f * inv);
-  }
-  if (tid == 0) p.counters[item] = 0;
+  // merge scratch: [4][16][128] + [4][16][2] floats = 33 KB of the (drained) 51 KB pipeline ring
+  split_kv_finish<D8_ROWS>(p.ws, item, split, p.splits_full, rows_total, reinterpret_cast<float*>(smem),
+                           reinterpret_cast<float*>(smem + 32 * 1024), &s_is_last,
+                           [&](int r, int d, float v0, float v1, float, float) { store_row_elem(r, d, v0, v1); });
   DUO_TRACE_STAMP(3);
 }
 
@@ -1143,18 +1046,14 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
   p.splits_full = splits;
   p.keys_per_split = (int)kps;
   const long long items = (long long)d.batch * d.n_full * p.n_rb;
-  const size_t need_o = (size_t)items * splits * ROWS * 128 * 4;
-  const size_t need_ml = (size_t)items * splits * ROWS * 2 * 4;
-  const size_t need_cnt = (size_t)(items + 1) * 4;
-  if (splits > 1 && (workspace == nullptr || workspace_bytes < need_o + need_ml + need_cnt + 1024)) {
-    set_error("duo_attention(int4): workspace too small (%zu < %zu)", workspace_bytes, need_o + need_ml + need_cnt + 1024);
-    return DUO_EWORKSPACE;
+  const size_t need = split_ws_bytes(items, splits, ROWS);
+  if (splits > 1) {
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("duo_attention(int4): workspace too small (%zu < %zu)", workspace_bytes, need);
+      return DUO_EWORKSPACE;
+    }
+    p.ws = split_ws_carve(workspace, items, splits, ROWS);
   }
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  p.counters = reinterpret_cast<int*>(ws);
-  const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
-  p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
-  p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
   const int grid_x = d.n_full * p.n_rb * splits + d.n_stream * p.n_rb;
   if (grid_x == 0) return DUO_OK;
   auto kern = duo_attn_int4_kernel<KEY_WARPS>;
@@ -1230,19 +1129,14 @@ static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const v
   p.splits_full = splits;
   p.keys_per_split = (int)kps;
   const long long items = (long long)d.batch * d.n_full;
-  const size_t need_o = (size_t)items * splits * D8_ROWS * 128 * 4;
-  const size_t need_ml = (size_t)items * splits * D8_ROWS * 2 * 4;
-  const size_t need_cnt = (size_t)(items + 1) * 4;
-  if (splits > 1 && (workspace == nullptr || workspace_bytes < need_o + need_ml + need_cnt + 1024)) {
-    set_error("duo_attention(int4/dec8): workspace too small (%zu < %zu)", workspace_bytes,
-              need_o + need_ml + need_cnt + 1024);
-    return DUO_EWORKSPACE;
+  const size_t need = split_ws_bytes(items, splits, D8_ROWS);
+  if (splits > 1) {
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("duo_attention(int4/dec8): workspace too small (%zu < %zu)", workspace_bytes, need);
+      return DUO_EWORKSPACE;
+    }
+    p.ws = split_ws_carve(workspace, items, splits, D8_ROWS);
   }
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  p.counters = reinterpret_cast<int*>(ws);
-  const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
-  p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
-  p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
   const int grid_x = d.n_full * splits + d.n_stream;
   if (grid_x == 0) return DUO_OK;
   static unsigned long long attr_mask = 0;  // four CTAs of 51 KB per SM: also ask for the full smem carve-out

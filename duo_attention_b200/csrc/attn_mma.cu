@@ -44,9 +44,7 @@ struct AttnParams {
   int keys_per_split;    // multiple of TILE
   int n_rb;              // row blocks per kv head
   int cache_scan;        // streaming: slots [0, cache_scan) are scanned
-  float* ws_o;           // [batch][n_full][n_rb][splits][ROWS][128]
-  float* ws_ml;          // [batch][n_full][n_rb][splits][ROWS][2]
-  int* counters;         // [batch][n_full][n_rb]
+  SplitWs ws;            // split-KV partials + arrival counters (duo_common.cuh)
   // partial mode (duo_attention_partial / duo_attention_seq): retrieval heads write the fp32 normalised O + log2-domain
   // log-sum-exp of THIS slice of their cache per (token, q head) instead of `out`.
   //   no_causal = 1 (duo_attention_partial): every query row sees all `full_len` keys; only retrieval heads launched
@@ -567,73 +565,21 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     return;
   }
 
-  // ---- split-KV: publish the partial, last CTA of this (batch, head, row block) merges ------------
+  // ---- split-KV: publish the partial; group / final merges by the last arrivals (split_kv_finish) ----------------
   const long long item = ((long long)b * p.n_full + kvh) * p.n_rb + rb;
-  float* wo = p.ws_o + (item * p.splits_full + split) * (long long)(ROWS * 128);
-  float* wml = p.ws_ml + (item * p.splits_full + split) * (long long)(ROWS * 2);
+  float* wo = p.ws.ws_o + (item * p.splits_full + split) * (long long)(ROWS * 128);
+  float* wml = p.ws.ws_ml + (item * p.splits_full + split) * (long long)(ROWS * 2);
   for (int idx = tid; idx < rows_here * 32; idx += ATTN_THREADS) {
     const int r = idx >> 5, d4 = (idx & 31) * 4;
     *reinterpret_cast<float4*>(&wo[r * 128 + d4]) = *reinterpret_cast<const float4*>(&sm_o[r * 128 + d4]);
   }
   if (tid < rows_here * 2) wml[tid] = sm_ml[tid];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int prev = atomicAdd(&p.counters[item], 1);
-    s_is_last = (prev == p.splits_full - 1);
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  // Parallel merge: warp w takes splits w, w+4, ... (lane = 4 output dims) and merges them online, then the 4 warps'
-  // partials are merged through shared memory.
-  const float* po = p.ws_o + item * p.splits_full * (long long)(ROWS * 128);
-  const float* pml = p.ws_ml + item * p.splits_full * (long long)(ROWS * 2);
-  float* cm_o = reinterpret_cast<float*>(smem);               // [4 warps][16][128]  (rows in groups of 16)
-  float* cm_ml = reinterpret_cast<float*>(smem + 80 * 1024);  // [4 warps][16][2]
-  for (int rg = 0; rg < rows_here; rg += 16) {
-  const int rg_n = min(16, rows_here - rg);
-  // four rows per pass: 16 independent 512 B loads in flight per warp (split_merge_rows4); the row-at-a-time loop it
-  // replaced cost splits/16 dependent L2 round trips per row (~25 us of a single-retrieval-head launch)
-  for (int rr0 = 0; rr0 < rg_n; rr0 += 4) {
-    const int nr = min(4, rg_n - rr0);
-    float4 acc4[4];
-    float mm4[4], ll4[4];
-    split_merge_rows4<ROWS>(po, pml, p.splits_full, warp, lane, rg + rr0, nr, acc4, mm4, ll4);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (q < nr) {
-        *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr0 + q) * 128 + lane * 4]) = acc4[q];
-        if (lane == 0) {
-          cm_ml[(warp * 16 + rr0 + q) * 2] = mm4[q];
-          cm_ml[(warp * 16 + rr0 + q) * 2 + 1] = ll4[q];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < rg_n * 64; idx += ATTN_THREADS) {
-    const int rr = idx >> 6, d = (idx & 63) * 2;
-    float mm = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) mm = fmaxf(mm, cm_ml[(w * 16 + rr) * 2]);
-    float a0f = 0.f, a1f = 0.f, ll = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float mw = cm_ml[(w * 16 + rr) * 2];
-      if (mw == -INFINITY) continue;
-      const float f = fast_exp2(mw - mm);
-      a0f += f * cm_o[(w * 16 + rr) * 128 + d];
-      a1f += f * cm_o[(w * 16 + rr) * 128 + d + 1];
-      ll += f * cm_ml[(w * 16 + rr) * 2 + 1];
-    }
-    const float inv = ll > 0.f ? 1.f / ll : 0.f;
-    store_row_elem(rg + rr, d, a0f * inv, a1f * inv);
-    if (p.part_lse && d == 0) store_row_lse(rg + rr, mm, ll);
-  }
-  __syncthreads();
-  }
-  if (tid == 0) p.counters[item] = 0;  // leave the workspace ready for the next launch
+  split_kv_finish<ROWS>(p.ws, item, split, p.splits_full, rows_here, reinterpret_cast<float*>(smem),
+                        reinterpret_cast<float*>(smem + 80 * 1024), &s_is_last,
+                        [&](int r, int d, float v0, float v1, float mm, float ll) {
+                          store_row_elem(r, d, v0, v1);
+                          if (p.part_lse && d == 0) store_row_lse(r, mm, ll);
+                        });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -642,15 +588,15 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
 constexpr int ATTN_SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 
 size_t mma_workspace_bytes(int batch, int n_kv, int group, int max_q_len) {
-  // The launcher never creates more than ~2 CTAs/SM worth of split partials (items * splits <= budget),
-  // each at most 64 rows x (128 + 2) floats; counters: one per (batch, kv head, row block).
-  const long long max_partials = 2 * 160 + 64;
+  // The launchers never create more than ~4 CTAs/SM worth of split partials (items * splits <= budget), each at most
+  // 64 rows x (128 + 2) floats, plus one level-2 partial per group of kMergeGroup splits and per item, plus counters.
+  const long long max_partials = 4 * 160 + 64;
   const long long rows = (long long)group * max_q_len;
   const long long items = (long long)batch * n_kv * ((rows + 15) / 16);
-  const long long o = max_partials * 64 * 128 * 4;
-  const long long ml = max_partials * 64 * 2 * 4;
-  const long long cnt = (items + 1) * 4;
-  return (size_t)(o + ml + cnt + 4096);
+  const long long l1 = max_partials * 64 * 130 * 4;
+  const long long l2 = (max_partials / kMergeGroup + items + 8) * 64 * 130 * 4;
+  const long long cnt = (2 * items + max_partials / kMergeGroup + 64) * 4;
+  return (size_t)(l1 + l2 + cnt + 8192);
 }
 
 struct PartialMode {      // how the retrieval heads report (see AttnParams)
@@ -742,21 +688,14 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   p.keys_per_split = (int)kps;
 
   const long long items = (long long)d.batch * d.n_full * p.n_rb;
-  const size_t need_o = (size_t)items * splits * ROWS * 128 * 4;
-  const size_t need_ml = (size_t)items * splits * ROWS * 2 * 4;
-  const size_t need_cnt = (size_t)(items + 1) * 4;
+  const size_t need = split_ws_bytes(items, splits, ROWS);
   if (splits > 1) {
-    if (workspace == nullptr || workspace_bytes < need_o + need_ml + need_cnt + 256) {
-      set_error("duo_attention: workspace too small (%zu < %zu)", workspace_bytes, need_o + need_ml + need_cnt + 256);
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("duo_attention: workspace too small (%zu < %zu)", workspace_bytes, need);
       return DUO_EWORKSPACE;
     }
+    p.ws = split_ws_carve(workspace, items, splits, ROWS);
   }
-  // counters first (they must stay zero between launches; O/ml partials need no initialisation)
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  p.counters = reinterpret_cast<int*>(ws);
-  const size_t cnt_bytes = (need_cnt + 255) / 256 * 256;
-  p.ws_ml = reinterpret_cast<float*>(ws + cnt_bytes);
-  p.ws_o = reinterpret_cast<float*>(ws + cnt_bytes + (need_ml + 255) / 256 * 256);
 
   const int grid_x = d.n_full * p.n_rb * splits + (partial ? 0 : d.n_stream * p.n_rb);
   if (grid_x == 0) return DUO_OK;

