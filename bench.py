@@ -48,10 +48,18 @@ ARCHS = {
                            max_position_embeddings=32768), "Llama-2-7B-32K-Instruct"),
 }
 SINK, RECENT = 64, 256
-# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the decode kernel, divided by the
-# algorithmic bytes of that launch (profiles/r1_decode.md: 3.2224 GB + 0.0040 GB measured for the n_full = 6 layer
-# at 1,048,576 tokens whose algorithmic traffic is 3.2212 GB; 2.1489 GB vs 2.1475 GB for an n_full = 4 layer)
-NCU_DECODE_TRAFFIC_RATIO = 1.0016
+
+
+def ncu_traffic(kind):
+    """DRAM traffic of the dominant kernel from THIS round's `ncu --set full` capture (profiles/r2_traffic.json, written by
+    profiles/summarize.py from the .ncu-rep of profiles/capture.sh): {"dram_bytes": read+write of the captured launch,
+    "algorithmic_bytes": algorithmic bytes of that same launch}.  None if the capture has not been summarised."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[kind]
+        return d
+    except Exception:
+        return None
+
 METRIC = "decode tok/s @1M ctx (+ prefill tok/s @128K in `prefill`), Llama-3-8B, DuoAttention 50% retrieval heads"
 
 
@@ -136,9 +144,12 @@ def cpu_reference_sample(ctx, mask, threads=None):
     q = torch.randn(1, 1, G, D, generator=g).to(torch.bfloat16)
     k = torch.randn(1, ctx + 1, 1, D, generator=g).to(torch.bfloat16)
     v = torch.randn(1, ctx + 1, 1, D, generator=g).to(torch.bfloat16)
-    t0 = time.perf_counter()
-    O.flash_attn_contract(q, k, v, causal=True)
-    t_full = time.perf_counter() - t0
+    samples = []
+    for _ in range(3):  # median of three: one cold sample swings 4x between boxes
+        t0 = time.perf_counter()
+        O.flash_attn_contract(q, k, v, causal=True)
+        samples.append(time.perf_counter() - t0)
+    t_full = sorted(samples)[1]
     ks, vs = k[:, : SINK + RECENT + 1], v[:, : SINK + RECENT + 1]
     t0 = time.perf_counter()
     for _ in range(10):
@@ -167,9 +178,9 @@ def run_reference(args):
         return
     mask, sp = head_pattern(args.pattern, args.sparsity)
     vals = []
-    for _ in range(max(1, min(args.steps, 3))):
+    for _ in range(max(1, min(args.steps, 5))):
         vals.append(cpu_reference_sample(args.ctx, mask))
-    best = max(vals, key=lambda r: r["tok_s"])
+    best = sorted(vals, key=lambda r: r["tok_s"])[len(vals) // 2]  # median of the samples, not the best
     line = {
         "impl": "reference", "metric": METRIC, "value": best["tok_s"], "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / best["tok_s"], "higher_is_better": True,
@@ -374,7 +385,7 @@ def main():
             prefill_once(False)  # warm-up (cuBLAS heuristics, TMA descriptors, allocator)
             barrier()
             c0 = cache.launch_count + ops.LAUNCHES
-            times = []
+            times, attn_times = [], []
             for _ in range(args.prefill_reps):
                 cache.profile_events = []
                 barrier()
@@ -386,20 +397,24 @@ def main():
                 barrier()
                 torch.cuda.nvtx.range_pop()
                 times.append(max_over_ranks(e0.elapsed_time(e1)))
-                attn_ms = sum(a.elapsed_time(b) for a, b in cache.profile_events)
+                attn_times.append(sum(a.elapsed_time(b) for a, b in cache.profile_events))
             cache.profile_events = None
             launches_prefill = cache.launch_count + ops.LAUNCHES - c0
-        ms = min(times)
+        best = min(range(len(times)), key=lambda i: times[i])
+        ms = times[best]
         fl = prefill_flops(mask, args.prefill_ctx, args.chunk, G=32 // mask.shape[1])
         peaks = load_peaks()
-        attn_ms = max_over_ranks(attn_ms)
+        attn_ms = max_over_ranks(attn_times[best])  # attention launches of the SAME repetition `ms` comes from
         result["prefill"] = {
             "value": args.prefill_ctx / (ms / 1e3), "unit": "tokens/s", "ms_per_prefill": ms, "reps": args.prefill_reps,
             "e2e": True, "h2d_bytes": int(args.prefill_ctx * 8), "d2h_bytes": 8,
             "roofline": {"bound": "tensor", "achieved": fl / world / (attn_ms / 1e3) / 1e12 if attn_ms else None,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (fl / world / (attn_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]) if attn_ms else None,
-                         "traffic": None, "attn_ms": attn_ms, "algorithmic_flops": fl,
+                         "traffic": (ncu_traffic("prefill") or {}).get("dram_bytes"),
+                         "traffic_note": "dram__bytes_read+write of ONE ncu-captured launch of duo_attn_tc_kernel (last 32K "
+                                         "chunk over 96K past, n_full=4: profiles/r2_prefill.md); compute-bound kernel",
+                         "attn_ms": attn_ms, "algorithmic_flops": fl,
                          "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)"},
             "gpu_launches": launches_prefill,
         }
@@ -515,6 +530,15 @@ def main():
         by = decode_bytes_per_token(local_mask, args.ctx, 68 if args.kv_format == "int4" else 256)  # this rank's bytes
     attn_ms_max = max_over_ranks(attn_ms)
     achieved = by / (attn_ms / 1e3) / 1e9
+    cap = ncu_traffic("decode_int4" if args.kv_format == "int4" else "decode")
+    traffic, traffic_note = None, "no ncu capture summarised for this round (profiles/r2_traffic.json missing)"
+    if cap:
+        # per average launch of THIS run: algorithmic bytes per launch x (DRAM bytes / algorithmic bytes) of the launch
+        # ncu captured this round — a run whose kernel re-read data would show up in the capture, not here
+        traffic = by / max(n_attn, 1) * cap["dram_bytes"] / cap["algorithmic_bytes"]
+        traffic_note = (f"algorithmic bytes per average launch x DRAM/algorithmic ratio "
+                        f"{cap['dram_bytes'] / cap['algorithmic_bytes']:.4f} of this round's ncu --set full capture "
+                        f"({cap.get('source', 'profiles/r2_decode.md')})")
     line = {
         "metric": METRIC, "value": 1e3 / ms_step, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -526,9 +550,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": (by / max(n_attn, 1) * NCU_DECODE_TRAFFIC_RATIO) if args.kv_format == "bf16" else None,
-                     "traffic_note": "bytes per average launch = algorithmic bytes per launch x the DRAM/algorithmic "
-                                     "ratio of the ncu --set full capture (profiles/r1_decode.md)",
+                     "traffic": traffic, "traffic_note": traffic_note,
                      "achieved_note": "algorithmic bytes of the 32 attention launches of a step / sum of their "
                                       "CUDA-event durations (eager pass on the launching stream)",
                      "kernel": ("duo_attn_int4_dec8_kernel" if args.kv_format == "int4" else "duo_attn_mma_kernel")

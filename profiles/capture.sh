@@ -12,7 +12,7 @@ NCU="ncu --clock-control none"
 COMMON="--steps 1 --warmup 3 --no-cpu-baseline --no-fa2 --no-graph"
 $NCU --nvtx --nvtx-include "timed_decode/" --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_decode.csv \
     python bench.py $COMMON --no-prefill > gpurun_out/ncu_decode_stdout.log 2>&1
-$NCU --set full --import-source on -k regex:duo_attn_mma_kernel -s 200 -c 2 -o gpurun_out/prof_decode \
+$NCU --set full --import-source on -k regex:duo_attn_mma_kernel -s 100 -c 2 -o gpurun_out/prof_decode \
     python bench.py $COMMON --no-prefill > gpurun_out/ncu_decode_full_stdout.log 2>&1
 $NCU --nvtx --nvtx-include "timed_prefill/" --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_prefill.csv \
     python bench.py $COMMON --prefill-reps 1 > gpurun_out/ncu_prefill_stdout.log 2>&1

@@ -7,7 +7,7 @@ import re
 import subprocess
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 OUT = "profiles"
 SRC = "gpurun_out"
 
@@ -101,17 +101,64 @@ def kernel_section(rep, title, note):
     return "\n".join(out)
 
 
-with open(f"{OUT}/{tag}_decode.md", "w") as f:
-    f.write(f"# {tag}: decode @1M ctx, Llama-3-8B pattern 0.5 (command: profiles/capture.sh)\n\n")
-    f.write(launch_table(f"{SRC}/launches_decode.csv", "Launch list of ONE timed decode step (nvtx range timed_decode)"))
-    f.write("\n")
-    f.write(kernel_section(f"{SRC}/prof_decode.ncu-rep", "`ncu --set full` of duo_attn_mma_kernel (3 launches)",
-                           "traffic = dram__bytes_read.sum + dram__bytes_write.sum; algorithmic bytes of a launch = "
-                           "n_full * (N+1) * 512 B (+ streaming heads, negligible)."))
-with open(f"{OUT}/{tag}_prefill.md", "w") as f:
-    f.write(f"# {tag}: prefill 128K in 32K chunks, Llama-3-8B pattern 0.5 (command: profiles/capture.sh)\n\n")
-    f.write(launch_table(f"{SRC}/launches_prefill.csv", "Launch list of ONE timed 128K prefill (nvtx range timed_prefill)"))
-    f.write("\n")
-    f.write(kernel_section(f"{SRC}/prof_prefill.ncu-rep", "`ncu --set full` of duo_attn_tc_kernel (2 launches, 4th chunk)",
-                           "Tensor-pipe utilisation = sm__ops_path_tensor_op_utchmma_* / TriageCompute.sm__pipe_tensor_cycles_active."))
-print("wrote", f"{OUT}/{tag}_decode.md", f"{OUT}/{tag}_prefill.md")
+import json
+import os
+
+CTX = 1048576
+
+
+def traffic_entry(rep, row_bytes, source):
+    """DRAM bytes of the first captured launch + the algorithmic bytes of that same launch (its number of retrieval
+    heads is recovered from the traffic itself: n_full = round(read / ((ctx + 1) * row_bytes)))."""
+    d = raw_metrics(rep)[0]
+
+    def val(name):
+        v, unit = d[name]
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    n_full = max(1, round(rd / ((CTX + 1) * row_bytes)))
+    alg = n_full * (CTX + 1) * row_bytes + (8 - n_full) * 321 * row_bytes
+    return {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "algorithmic_bytes": alg, "n_full_of_launch": n_full,
+            "source": source}
+
+
+traffic = {}
+if os.path.exists(f"{SRC}/prof_decode.ncu-rep"):
+    with open(f"{OUT}/{tag}_decode.md", "w") as f:
+        f.write(f"# {tag}: decode @1M ctx, Llama-3-8B pattern 0.5 (command: profiles/capture.sh)\n\n")
+        f.write(launch_table(f"{SRC}/launches_decode.csv", "Launch list of ONE timed decode step (nvtx range timed_decode)"))
+        f.write("\n")
+        f.write(kernel_section(f"{SRC}/prof_decode.ncu-rep", "`ncu --set full` of duo_attn_mma_kernel (fused decode step)",
+                               "traffic = dram__bytes_read.sum + dram__bytes_write.sum; algorithmic bytes of a launch = "
+                               "n_full * (N+1) * 512 B (+ streaming heads, negligible)."))
+    traffic["decode"] = traffic_entry(f"{SRC}/prof_decode.ncu-rep", 512, f"profiles/{tag}_decode.md")
+if os.path.exists(f"{SRC}/prof_prefill.ncu-rep"):
+    with open(f"{OUT}/{tag}_prefill.md", "w") as f:
+        f.write(f"# {tag}: prefill 128K in 32K chunks, Llama-3-8B pattern 0.5 (command: profiles/capture.sh)\n\n")
+        f.write(launch_table(f"{SRC}/launches_prefill.csv", "Launch list of ONE timed 128K prefill (nvtx range timed_prefill)"))
+        f.write("\n")
+        f.write(kernel_section(f"{SRC}/prof_prefill.ncu-rep", "`ncu --set full` of duo_attn_tc_kernel (last 32K chunk over 96K past, n_full = 4)",
+                               "Tensor-pipe utilisation = sm__ops_path_tensor_op_utchmma_* / TriageCompute.sm__pipe_tensor_cycles_active."))
+    d = raw_metrics(f"{SRC}/prof_prefill.ncu-rep")[0]
+    traffic["prefill"] = {"dram_bytes": sum(float(d[k][0].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(d[k][1], 1)
+                                            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")),
+                          "source": f"profiles/{tag}_prefill.md"}
+if os.path.exists(f"{SRC}/prof_int4_dec8.ncu-rep"):
+    with open(f"{OUT}/{tag}_int4.md", "w") as f:
+        f.write(f"# {tag}: INT4-KV decode @1M ctx, Llama-3-8B pattern 0.5 (command: profiles/capture_int4.sh)\n\n")
+        if os.path.exists(f"{SRC}/launches_int4.csv"):
+            f.write(launch_table(f"{SRC}/launches_int4.csv", "Launch list of ONE timed INT4 decode step"))
+            f.write("\n")
+        f.write(kernel_section(f"{SRC}/prof_int4_dec8.ncu-rep", "`ncu --set full` of duo_attn_int4_dec8_kernel",
+                               "algorithmic bytes of a launch = n_full * (N+1) * 2 * 68 B (64 B codes + fp16 scale + fp16 zero per "
+                               "row, K and V) + streaming heads (negligible)."))
+    traffic["decode_int4"] = traffic_entry(f"{SRC}/prof_int4_dec8.ncu-rep", 136, f"profiles/{tag}_int4.md")
+if traffic:
+    old = {}
+    if os.path.exists(f"{OUT}/{tag}_traffic.json"):
+        old = json.load(open(f"{OUT}/{tag}_traffic.json"))
+    old.update(traffic)
+    json.dump(old, open(f"{OUT}/{tag}_traffic.json", "w"), indent=1)
+print("wrote", [k for k in traffic], "->", f"{OUT}/{tag}_*.md / {tag}_traffic.json")
