@@ -595,8 +595,7 @@ size_t mma_workspace_bytes(int batch, int n_kv, int group, int max_q_len) {
   const long long items = (long long)batch * n_kv * ((rows + 15) / 16);
   const long long l1 = max_partials * 64 * 130 * 4;
   const long long l2 = (max_partials / kMergeGroup + items + 8) * 64 * 130 * 4;
-  const long long cnt = (2 * items + max_partials / kMergeGroup + 64) * 4;
-  return (size_t)(l1 + l2 + cnt + 8192);
+  return (size_t)(kSplitCounterBytes + l1 + l2 + 8192);
 }
 
 struct PartialMode {      // how the retrieval heads report (see AttnParams)

@@ -382,14 +382,6 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         consume(rb, 3);
         const bool outgrown = (mx - m_ref) * c > 8.0f;
         if (!__any_sync(0xffffffffu, outgrown)) {
-          // The PV product uses P rounded to T while l sums the unrounded p.  With an exact running max (FlashAttention-2)
-          // the largest term of a row is exactly 1 and rounds without error; under the lazy reference it is some
-          // 2^x <= 2^8 and its rounding error (up to 2^-9 relative) would dominate the error of sharp-softmax rows.
-          // Make l see the ROUNDED value of each tile's largest term, so that error cancels in O / l as it does there.
-          {
-            const float pm = fast_exp2(mx * c - mref_c);
-            rs += TcType<T>::lo(TcType<T>::pack(pm, 0.f)) - pm;
-          }
           uint32_t half0[32], half1[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -453,10 +445,6 @@ duo_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       const float mref_c = (m_ref == -INFINITY) ? 0.f : m_ref * c;
       float rs = 0.f;
-      if (mx != -INFINITY) {  // rounded largest term into l (see the fast path)
-        const float pm = fast_exp2(mx * c - mref_c);
-        rs = TcType<T>::lo(TcType<T>::pack(pm, 0.f)) - pm;
-      }
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t r[32];

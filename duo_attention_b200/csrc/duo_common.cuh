@@ -287,13 +287,19 @@ struct SplitWs {        // device pointers into the caller's workspace
 
 inline int split_groups(int splits) { return splits <= kMergeGroup ? 1 : (splits + kMergeGroup - 1) / kMergeGroup; }
 
-// bytes of workspace a launch with this geometry needs (0 if no split)
+// The arrival counters live in a FIXED region at the start of the workspace (they must stay zero between launches, and
+// launches of different geometry — layers with different numbers of retrieval heads, decode steps and chunks — share
+// one workspace: a geometry-dependent counter region would overlap partial data written by an earlier launch).
+constexpr size_t kSplitCounterBytes = 64 * 1024;
+
+// bytes of workspace a launch with this geometry needs (0 if no split); SIZE_MAX if it has too many counters
 inline size_t split_ws_bytes(long long items, int splits, int rows) {
   if (splits <= 1) return 0;
   const int ng = split_groups(splits);
+  if ((size_t)items * (1 + ng) * 4 > kSplitCounterBytes) return (size_t)-1;
   const size_t a = 256;
   auto up = [&](size_t x) { return (x + a - 1) / a * a; };
-  size_t tot = up((size_t)items * (1 + ng) * 4);
+  size_t tot = kSplitCounterBytes;
   tot += up((size_t)items * splits * rows * 2 * 4) + up((size_t)items * splits * rows * 128 * 4);
   if (ng > 1) tot += up((size_t)items * ng * rows * 2 * 4) + up((size_t)items * ng * rows * 128 * 4);
   return tot + 256;
@@ -306,8 +312,8 @@ inline SplitWs split_ws_carve(void* workspace, long long items, int splits, int 
   const size_t a = 256;
   auto up = [&](size_t x) { return (x + a - 1) / a * a; };
   uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
-  w.counters = reinterpret_cast<int*>(p);  // counters first: they must stay zero between launches
-  p += up((size_t)items * (1 + ng) * 4);
+  w.counters = reinterpret_cast<int*>(p);
+  p += kSplitCounterBytes;
   w.ws_ml = reinterpret_cast<float*>(p);
   p += up((size_t)items * splits * rows * 2 * 4);
   w.ws_o = reinterpret_cast<float*>(p);
