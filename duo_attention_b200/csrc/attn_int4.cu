@@ -552,6 +552,8 @@ constexpr int D8_STAGES = 3;
 constexpr int D8_PACK = D8_TILE * 64;
 constexpr int D8_STAGE_BYTES = 2 * D8_PACK + 4 * D8_TILE * 2;
 constexpr int D8_ROWS = 8;
+constexpr int D8_CHUNK_TILES = 8;                       // dynamic scheduling granule: 8 tiles = 1024 keys (~5 us of work)
+constexpr int D8_CHUNK_KEYS = D8_CHUNK_TILES * D8_TILE;
 constexpr int D8_SMEM_BYTES = D8_STAGES * D8_STAGE_BYTES + 128;
 static_assert(D8_STAGES * D8_STAGE_BYTES >= (4 * D8_ROWS * 128 + D8_ROWS * 128 + 5 * D8_ROWS * 2) * 4, "merge smem");
 
@@ -585,6 +587,7 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   __shared__ int s_is_last;
+  __shared__ int s_chunk[3];  // look-ahead ring of dynamically fetched chunk ids (retrieval heads)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -637,13 +640,54 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     gvs = p.rvs + hrow;
     gvz = p.rvz + hrow;
   }
+  // Tile schedule.  Retrieval heads with several CTAs pull CHUNKS of D8_CHUNK_TILES tiles from a per-head atomic counter
+  // (dynamic load balance: with a static split the slowest CTA finished ~35 % after the median one — per-CTA time in this
+  // latency-sensitive loop varies with the SM's distance to the data — and every other SM idled meanwhile).  A CTA's
+  // online-softmax partial does not care which keys it saw.  Streaming heads and single-CTA heads walk a static list.
+  const bool dyn = is_full && p.splits_full > 1;
+  const long long nkeys_full = p.full_len + tok_max + 1;
+  const int n_chunks = (int)((nkeys_full + D8_CHUNK_KEYS - 1) / D8_CHUNK_KEYS);
+  int* chunk_ctr = dyn ? p.ws.counters + ((long long)b * p.n_full + kvh) * (2 + p.ws.n_groups) + 1 + p.ws.n_groups : nullptr;
+  if (dyn) {
+    a0 = 0;
+    a1 = nkeys_full;
+  }
   const int nA = (int)((a1 - a0 + D8_TILE - 1) / D8_TILE);
   const int nB = (int)((b1 - b0 + D8_TILE - 1) / D8_TILE);
-  const int n_tiles = nA + nB;
-  auto tile_start = [&](int i) -> long long {
-    return i < nA ? a0 + (long long)i * D8_TILE : b0 + (long long)(i - nA) * D8_TILE;
+  const int n_static = nA + nB;
+  if (dyn) {
+    if (tid == 0) {
+      s_chunk[0] = atomicAdd(chunk_ctr, 1);
+      s_chunk[1] = atomicAdd(chunk_ctr, 1);
+    }
+    __syncthreads();
+  }
+  int sch_i = 0;                      // static: index of the next tile; dynamic: number of chunk switches so far
+  int sch_chunk = -1, sch_t = D8_CHUNK_TILES;
+  bool sch_done = false;
+  // key start of the next tile to load, or -1 when this CTA has no more tiles (uniform over the CTA)
+  auto next_tile = [&]() -> long long {
+    if (!dyn) {
+      if (sch_i >= n_static) return -1;
+      const int i = sch_i++;
+      return i < nA ? a0 + (long long)i * D8_TILE : b0 + (long long)(i - nA) * D8_TILE;
+    }
+    if (sch_done) return -1;
+    if (sch_t == D8_CHUNK_TILES) {  // next chunk: slot sch_i % 3 was filled >= one __syncthreads ago
+      sch_chunk = s_chunk[sch_i % 3];
+      if (tid == 0) s_chunk[(sch_i + 2) % 3] = atomicAdd(chunk_ctr, 1);  // read two switches from now
+      ++sch_i;
+      sch_t = 0;
+    }
+    const long long j0 = (long long)sch_chunk * D8_CHUNK_KEYS + (long long)sch_t * D8_TILE;
+    if (sch_chunk >= n_chunks || j0 >= nkeys_full) {
+      sch_done = true;
+      return -1;
+    }
+    ++sch_t;
+    return j0;
   };
-  auto tile_end = [&](int i) -> long long { return i < nA ? a1 : b1; };
+  auto tile_end_of = [&](long long j0) -> long long { return is_full ? a1 : (j0 < b0 ? a1 : b1); };
 
   // loader: same tile image as duo_attn_int4_kernel<4>.  Interior tiles (every row valid) take a path with one
   // address per thread and immediate offsets; boundary tiles predicate and zero-fill per row.
@@ -652,11 +696,10 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
   const int ld_arr = (tid & 63) >> 4, ld_qd = tid & 15;  // scale/zero arrays: 4 arrays x 16 chunks of 8 rows
   const __half* ld_src = ld_arr == 0 ? gks : ld_arr == 1 ? gkz : ld_arr == 2 ? gvs : gvz;
   const uint32_t ld_soff = 2 * D8_PACK + ld_arr * (D8_TILE * 2) + ld_qd * 16;
-  auto issue = [&](int i) {
-    if (i < n_tiles) {
-      const long long j0 = tile_start(i);
-      const long long lim = min(tile_end(i), slots);  // rows >= lim are not read (zero-filled)
-      const uint32_t sbase = smem_u32(smem + (i % D8_STAGES) * D8_STAGE_BYTES);
+  auto issue = [&](int stage, long long j0) {
+    if (j0 >= 0) {
+      const long long lim = min(tile_end_of(j0), slots);  // rows >= lim are not read (zero-filled)
+      const uint32_t sbase = smem_u32(smem + stage * D8_STAGE_BYTES);
       if (j0 + D8_TILE <= lim) {
         const long long off = (j0 + ld_r0) * 64 + ld_c * 16;
         const uint8_t* kp = gk + off;
@@ -686,8 +729,10 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     }
     cp_async_commit();
   };
-#pragma unroll
-  for (int i = 0; i < D8_STAGES - 1; ++i) issue(i);
+  static_assert(D8_STAGES == 3, "the tile queue below holds STAGES - 1 = 2 tiles in flight");
+  long long q_cur = next_tile(), q_nxt = next_tile();  // key starts of the tiles in flight (registers, uniform)
+  issue(0, q_cur);
+  issue(1, q_nxt);
 
   // ---- Q^T as B fragments: lane (g, t4) holds query row g, head_dim chunk 32 t4 .. 32 t4 + 31 ------------
   const int wkey = warp * KPW;
@@ -745,15 +790,19 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
   const uint32_t ones[4] = {0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u};
   const int lrow = lane & 7, lmat = lane >> 3;
 
-  for (int i = 0; i < n_tiles; ++i) {
+  for (int i = 0; q_cur >= 0; ++i) {
     cp_async_wait<D8_STAGES - 2>();
     __syncthreads();
-    issue(i + D8_STAGES - 1);
+    const long long q_new = next_tile();
+    issue((i + D8_STAGES - 1) % D8_STAGES, q_new);
     const uint8_t* st = smem + (i % D8_STAGES) * D8_STAGE_BYTES;
     const uint32_t sK = smem_u32(st), sV = sK + D8_PACK;
     const uint32_t sKs = sK + 2 * D8_PACK, sKz = sKs + 2 * D8_TILE, sVs = sKs + 4 * D8_TILE, sVz = sKs + 6 * D8_TILE;
-    const long long j0 = tile_start(i);
-    const long long jend = tile_end(i);
+    const long long j0 = q_cur;
+    const long long jend = tile_end_of(j0);
+    const bool a_seg = !is_full && j0 < b0;  // sink / ring slots of a streaming head: per-slot validity
+    q_cur = q_nxt;
+    q_nxt = q_new;
 
     // ---- S^T_raw = codes(K) . Q^T : 2 m-tiles of 16 keys ----------------------------------------------------
     float sc[2][4];
@@ -777,7 +826,7 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     }
     // ---- logits s_j (S_raw - qoff) + z_j qsum; mask on boundary tiles -----------------------------------------
     const long long kfirst = j0 + wkey;
-    const bool need_mask = (kfirst + KPW > jend) || (kfirst + KPW - 1 > base) || (!is_full && i < nA);
+    const bool need_mask = (kfirst + KPW > jend) || (kfirst + KPW - 1 > base) || a_seg;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -795,7 +844,7 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
         for (int hk = 0; hk < 2; ++hk) {
           const long long j = kfirst + mt * 16 + hk * 8 + g;
           bool kvis = j < jend;
-          if (!is_full && i < nA) kvis = kvis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
+          if (a_seg) kvis = kvis && stream_slot_valid((int)j, p.sink, p.recent, p.total, p.lo);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int tk = tok_r[e];

@@ -129,11 +129,27 @@ __device__ __forceinline__ void rope2(uint32_t& lo2, uint32_t& hi2, const void* 
   }
 }
 
+// Debug build only (`make trace`, -DDUO_TRACE): per-CTA %globaltimer stamps (profiles/int4_trace.py)
+#ifdef DUO_TRACE
+__device__ unsigned long long* g_duo_trace_mma = nullptr;
+__device__ __forceinline__ void trace_stamp_mma(int slot) {
+  if (threadIdx.x == 0 && g_duo_trace_mma) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_duo_trace_mma[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 4 + slot] = t;
+  }
+}
+#define DUO_TRACE_MMA(slot) trace_stamp_mma(slot)
+#else
+#define DUO_TRACE_MMA(slot)
+#endif
+
 template <typename T, int KEY_WARPS, bool FUSED>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
 duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_constant__ CUtensorMap map_fv,
                     const __grid_constant__ CUtensorMap map_rk, const __grid_constant__ CUtensorMap map_rv,
                     const AttnParams pin) {
+  DUO_TRACE_MMA(0);
   AttnParams p = pin;
   if (pin.dstate) {  // occupancy lives in device memory: recompute everything that depends on it
     p.full_len = pin.dstate[0];
@@ -470,6 +486,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     }
   }
 
+  DUO_TRACE_MMA(1);
   // row sums live distributed over the 4 lanes of a quad
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
@@ -574,12 +591,14 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     *reinterpret_cast<float4*>(&wo[r * 128 + d4]) = *reinterpret_cast<const float4*>(&sm_o[r * 128 + d4]);
   }
   if (tid < rows_here * 2) wml[tid] = sm_ml[tid];
+  DUO_TRACE_MMA(2);
   split_kv_finish<ROWS>(p.ws, item, split, p.splits_full, rows_here, reinterpret_cast<float*>(smem),
                         reinterpret_cast<float*>(smem + 80 * 1024), &s_is_last,
                         [&](int r, int d, float v0, float v1, float mm, float ll) {
                           store_row_elem(r, d, v0, v1);
                           if (p.part_lse && d == 0) store_row_lse(r, mm, ll);
                         });
+  DUO_TRACE_MMA(3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -788,6 +807,12 @@ int launch_attn_mma_partial(const duo_layer* L, long long n_keys, const void* q,
   return launch_variant<__half, 4>(L, &st, q, q_row_stride, nullptr, q_len, scale, workspace, workspace_bytes, stream,
                                    pm);
 }
+
+#ifdef DUO_TRACE
+extern "C" __attribute__((visibility("default"))) int duo_debug_set_trace_mma(void* buf) {
+  return cudaMemcpyToSymbol(g_duo_trace_mma, &buf, sizeof(void*)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 // One decode-sized chunk, everything in one launch (duo_decode_fused): RoPE(q, k) + KV append + mixed-head attention +
 // ring commit.  `qkv` is the raw fused projection output; it is NOT modified.

@@ -16,9 +16,10 @@ from duo_attention_b200.kv_cache import DuoKVCache  # noqa: E402
 dev = torch.device("cuda:0")
 lib = _C.load()
 lib.duo_debug_set_trace.argtypes = [C.c_void_p]
+lib.duo_debug_set_trace_mma.argtypes = [C.c_void_p]
 Hq, Hkv, D, sink, recent = 32, 8, 128, 64, 256
 for kvf, dtype in (("int4", torch.float16), ("same", torch.bfloat16)):
-    for n_full, N in ((1, 1 << 20), (2, 1 << 20), (4, 1 << 20), (4, 1 << 17), (8, 1 << 20)):
+    for n_full, N in ((1, 1 << 20), (2, 1 << 20), (4, 1 << 20), (4, 1 << 17), (4, 1 << 16), (8, 1 << 20)):
         cache = DuoKVCache(1, Hq, Hkv, D, [n_full], 1, N + 8, sink, recent, dtype, dev, kv_format=kvf)
         t = cache.tensors[0]
         g = torch.Generator(device=dev).manual_seed(0)
@@ -38,8 +39,12 @@ for kvf, dtype in (("int4", torch.float16), ("same", torch.bfloat16)):
         trace = torch.zeros(4096 * 4, dtype=torch.int64, device=dev)
 
         def run():
-            _C.check(lib.duo_attention(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), 1, D ** -0.5,
-                                       cache.workspace.data_ptr(), cache.workspace.numel(), stream))
+            if kvf == "int4":
+                _C.check(lib.duo_attention(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), 1, D ** -0.5,
+                                           cache.workspace.data_ptr(), cache.workspace.numel(), stream))
+            else:  # the product's decode path: one fused launch (RoPE off: q/k already rotated in this micro-benchmark)
+                _C.check(lib.duo_decode_fused(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), None, None, 0, out.data_ptr(),
+                                              1, D ** -0.5, cache.workspace.data_ptr(), cache.workspace.numel(), stream))
 
         for _ in range(3):
             run()
@@ -52,12 +57,13 @@ for kvf, dtype in (("int4", torch.float16), ("same", torch.bfloat16)):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         line = f"{kvf:5s} n_full={n_full} ctx={N:8d}: {ms*1e3:7.1f} us/launch"
-        if kvf == "int4":
-            lib.duo_debug_set_trace(trace.data_ptr())
+        if True:
+            setter = lib.duo_debug_set_trace if kvf == "int4" else lib.duo_debug_set_trace_mma
+            setter(trace.data_ptr())
             trace.zero_()
             run()
             torch.cuda.synchronize()
-            lib.duo_debug_set_trace(None)
+            setter(None)
             tr = trace.view(-1, 4).cpu()
             tr = tr[tr[:, 0] > 0]
             t0 = tr[:, 0].min()
