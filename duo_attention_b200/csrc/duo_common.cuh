@@ -277,8 +277,7 @@ __device__ __forceinline__ void split_merge_rows4(const float* po, const float* 
 constexpr int kMergeGroup = 16;
 
 struct SplitWs {        // device pointers into the caller's workspace
-  int* counters;        // [items][2 + n_groups]: top-level arrival count, one per group, then a work-queue cursor for
-                        // kernels that pull key chunks dynamically; all zero between launches
+  int* counters;        // [items][1 + n_groups]  (top-level arrival count, then one per group); zero between launches
   float* ws_ml;         // [items][splits][ROWS][2]
   float* ws_o;          // [items][splits][ROWS][128]
   float* g_ml;          // [items][n_groups][ROWS][2]     level-2 partials
@@ -297,7 +296,7 @@ constexpr size_t kSplitCounterBytes = 64 * 1024;
 inline size_t split_ws_bytes(long long items, int splits, int rows) {
   if (splits <= 1) return 0;
   const int ng = split_groups(splits);
-  if ((size_t)items * (2 + ng) * 4 > kSplitCounterBytes) return (size_t)-1;
+  if ((size_t)items * (1 + ng) * 4 > kSplitCounterBytes) return (size_t)-1;
   const size_t a = 256;
   auto up = [&](size_t x) { return (x + a - 1) / a * a; };
   size_t tot = kSplitCounterBytes;
@@ -382,7 +381,7 @@ __device__ __forceinline__ void split_kv_finish(const SplitWs& w, long long item
                                                 float* cm_o, float* cm_ml, int* s_flag, EmitFinal emit_final) {
   const int tid = threadIdx.x;
   const int ng = w.n_groups;
-  int* cnt = w.counters + item * (2 + ng);
+  int* cnt = w.counters + item * (1 + ng);
   const float* po = w.ws_o + item * splits * (long long)(ROWS * 128);
   const float* pml = w.ws_ml + item * splits * (long long)(ROWS * 2);
   auto final_emit = [&](int r, int d, float a0, float a1, float mm, float ll) {
@@ -397,7 +396,7 @@ __device__ __forceinline__ void split_kv_finish(const SplitWs& w, long long item
     if (!*s_flag) return;
     __threadfence();
     merge_partials_cta<ROWS>(po, pml, splits, rows, cm_o, cm_ml, final_emit);
-    if (tid == 0) cnt[0] = cnt[1 + ng] = 0;  // leave the workspace ready for the next launch
+    if (tid == 0) cnt[0] = 0;  // leave the workspace ready for the next launch
     return;
   }
   const int grp = split / kMergeGroup;
@@ -427,7 +426,7 @@ __device__ __forceinline__ void split_kv_finish(const SplitWs& w, long long item
   __threadfence();
   merge_partials_cta<ROWS>(w.g_o + item * ng * (long long)(ROWS * 128), w.g_ml + item * ng * (long long)(ROWS * 2), ng, rows,
                            cm_o, cm_ml, final_emit);
-  if (tid == 0) cnt[0] = cnt[1 + ng] = 0;
+  if (tid == 0) cnt[0] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
