@@ -22,7 +22,7 @@ DECODE_MAX_Q = 16
 SYMBOLS = [
     "duo_layer_create", "duo_layer_destroy", "duo_workspace_bytes", "duo_rope_append", "duo_attention",
     "duo_attention_mma", "duo_decode_fused", "duo_state_advance", "duo_state_set", "duo_stream_commit", "duo_quant_int4", "duo_dequant_int4", "duo_add_rmsnorm", "duo_silu_mul",
-    "duo_attention_partial", "duo_merge_partials", "duo_attention_seq",
+    "duo_attention_partial", "duo_merge_partials", "duo_attention_seq", "duo_decode_fused_seq",
     "duo_seqcomm_data_bytes", "duo_seqcomm_flag_bytes", "duo_seqcomm_create", "duo_seqcomm_destroy", "duo_seq_merge",
     "duo_comm_data_bytes", "duo_comm_flag_bytes", "duo_comm_create", "duo_comm_destroy", "duo_allreduce_add_rmsnorm",
     "duo_last_error_string", "duo_version",
@@ -105,6 +105,8 @@ def load():
     lib.duo_attention_partial.restype = C.c_int
     lib.duo_attention_seq.argtypes = [vp, C.POINTER(CacheState), vp, i64, vp, vp, vp, i32, f32, vp, sz, vp]
     lib.duo_attention_seq.restype = C.c_int
+    lib.duo_decode_fused_seq.argtypes = [vp, C.POINTER(CacheState), vp, i64, vp, vp, i32, vp, vp, vp, f32, vp, sz, vp]
+    lib.duo_decode_fused_seq.restype = C.c_int
     lib.duo_seqcomm_data_bytes.argtypes = [i32, i32]
     lib.duo_seqcomm_data_bytes.restype = sz
     lib.duo_seqcomm_flag_bytes.argtypes = [i32, i32]

@@ -64,6 +64,9 @@ int launch_attn_mma_seq(const duo_layer* L, const duo_cache_state* st, const voi
 int launch_decode_fused(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
                         const void* cos, const void* sin, int rope_mode, void* out, int q_len, float scale,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_decode_fused_seq(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
+                            const void* cos, const void* sin, int rope_mode, void* out, float* part_o, float* part_lse,
+                            float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_merge_partials(const float* o_parts, const float* lse_parts, int n_parts, long long tokens, int heads_total,
                           int heads_used, void* out, int dtype, cudaStream_t stream);
 int launch_add_rmsnorm(const void* x, const void* residual, const void* weight, void* out_norm, void* out_res,
@@ -306,6 +309,31 @@ int duo_decode_fused(const duo_layer* layer, const duo_cache_state* st, const vo
   }
   return launch_decode_fused(layer, st, qkv, qkv_row_stride, cos, sin, rope_mode, out, q_len, scale, workspace,
                              workspace_bytes, (cudaStream_t)stream);
+}
+
+int duo_decode_fused_seq(const duo_layer* layer, const duo_cache_state* st, const void* qkv, int64_t qkv_row_stride,
+                         const void* cos, const void* sin, int32_t rope_mode, void* out, float* out_o, float* out_lse,
+                         float scale, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_chunk(layer, st, 1, "duo_decode_fused_seq");
+  if (rc) return rc;
+  if (!qkv || !out || !out_o || !out_lse || (rope_mode != DUO_ROPE_NONE && (!cos || !sin))) {
+    set_error("duo_decode_fused_seq: null buffer");
+    return DUO_EINVAL;
+  }
+  if (rope_mode < DUO_ROPE_NONE || rope_mode > DUO_ROPE_FP32 || st->seq_world < 2) {
+    set_error("duo_decode_fused_seq: bad rope_mode %d or no sequence-shard descriptor", rope_mode);
+    return DUO_EINVAL;
+  }
+  if (layer->d.kv_format != DUO_KV_SAME || layer->d.group > 16) {
+    set_error("duo_decode_fused_seq: 16-bit caches and group <= 16 only");
+    return DUO_EINVAL;
+  }
+  if (qkv_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(qkv) & 15)) {
+    set_error("duo_decode_fused_seq: qkv rows must be 16-byte aligned (row stride a multiple of 8 elements)");
+    return DUO_EINVAL;
+  }
+  return launch_decode_fused_seq(layer, st, qkv, qkv_row_stride, cos, sin, rope_mode, out, out_o, out_lse, scale, workspace,
+                                 workspace_bytes, (cudaStream_t)stream);
 }
 
 // test / tuning hook: force the mma.sync kernel family even for shapes the tcgen05 kernel takes

@@ -155,9 +155,9 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
     p.full_len = pin.dstate[0];
     p.total = pin.dstate[1];
     p.lo = pin.dstate[2];
-    const long long nk = FUSED ? p.full_len
-                         : p.seq_world > 1 ? seq_local_len(p.full_len + p.q_len, p.seq_rank, p.seq_world, p.seq_block)
-                                           : p.full_len + p.q_len;
+    const long long nk = p.seq_world > 1
+                             ? seq_local_len(p.full_len + (FUSED ? 0 : p.q_len), p.seq_rank, p.seq_world, p.seq_block)
+                             : p.full_len + (FUSED ? 0 : p.q_len);
     long long kps = (nk + p.splits_full - 1) / p.splits_full;
     kps = (kps + TILE - 1) / TILE * TILE;
     p.keys_per_split = (int)(kps < TILE ? TILE : kps);
@@ -217,12 +217,16 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
   bool has_new = false;
   long long new_base = 0;  // key index of the first new token in this CTA's key index space
   if (is_full) {
-    const long long nkeys = FUSED ? p.full_len : vis_count(tok_max);
+    // cached rows of this rank's slice (all of them when the cache is not sequence-sharded)
+    const long long cached = p.seq_world > 1 ? seq_local_len(p.full_len, p.seq_rank, p.seq_world, p.seq_block) : p.full_len;
+    const long long nkeys = FUSED ? cached : vis_count(tok_max);
     a0 = (long long)split * p.keys_per_split;
     a1 = min(nkeys, a0 + (long long)p.keys_per_split);
     if (a1 < a0) a1 = a0;
     has_new = FUSED && (split == p.splits_full - 1);
-    new_base = p.full_len;
+    if (FUSED && p.seq_world > 1)  // one new token (q_len == 1): only its owner appends and attends it
+      has_new = has_new && ((int)((p.full_len / p.seq_block) % p.seq_world) == p.seq_rank);
+    new_base = cached;
   } else {
     a0 = 0;
     a1 = p.cache_scan;
@@ -335,7 +339,7 @@ duo_attn_mma_kernel(const __grid_constant__ CUtensorMap map_fk, const __grid_con
       const T* rows = reinterpret_cast<const T*>(p.q) + (long long)b * p.q_batch_stride;
       // destination row of new token r in the cache, or -1 if it is not kept (streaming: neither sink nor recent)
       auto dst_row = [&](int r) -> long long {
-        if (is_full) return ((long long)b * p.n_full + kvh) * p.full_cap + p.full_len + r;
+        if (is_full) return ((long long)b * p.n_full + kvh) * p.full_cap + new_base + r;  // (local) row of position full_len + r
         const long long pos = p.total + r;
         long long slot;
         if (pos < p.sink) slot = pos;
@@ -670,9 +674,9 @@ static int launch_variant(const duo_layer* L, const duo_cache_state* st, const v
   p.seq_rank = st->seq_rank;
   p.seq_world = st->seq_world;
   p.seq_block = st->seq_block;
-  const long long nkeys = (partial || FUSED) ? st->full_len
-                          : st->seq_world > 1 ? seq_local_len(st->full_len + q_len, st->seq_rank, st->seq_world, st->seq_block)
-                                              : st->full_len + q_len;
+  const long long seen = (partial || FUSED) ? st->full_len : st->full_len + q_len;  // positions the TMA tiles cover
+  const long long nkeys = (!partial && st->seq_world > 1) ? seq_local_len(seen, st->seq_rank, st->seq_world, st->seq_block)
+                                                          : seen;
   if (FUSED) {
     p.cos = fa.cos;
     p.sin = fa.sin;
@@ -828,6 +832,23 @@ int launch_decode_fused(const duo_layer* L, const duo_cache_state* st, const voi
                                                   stream, PartialMode(), fa);
   return launch_variant<__half, 4, true>(L, st, qkv, row_stride, out, q_len, scale, workspace, workspace_bytes, stream,
                                          PartialMode(), fa);
+}
+
+// duo_decode_fused for a sequence-sharded cache (ONE new token): as launch_decode_fused, retrieval heads report partials.
+int launch_decode_fused_seq(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
+                            const void* cos, const void* sin, int rope_mode, void* out, float* part_o, float* part_lse,
+                            float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  FusedArgs fa;
+  fa.cos = cos;
+  fa.sin = sin;
+  fa.rope_mode = rope_mode;
+  PartialMode pm;
+  pm.part_o = part_o;
+  pm.part_lse = part_lse;
+  if (L->d.dtype == DUO_DT_BF16)
+    return launch_variant<__nv_bfloat16, 4, true>(L, st, qkv, row_stride, out, 1, scale, workspace, workspace_bytes, stream,
+                                                  pm, fa);
+  return launch_variant<__half, 4, true>(L, st, qkv, row_stride, out, 1, scale, workspace, workspace_bytes, stream, pm, fa);
 }
 
 // Sequence-sharded decode step (duo_attention_seq): retrieval heads attend this rank's slice and report (O, lse)

@@ -537,25 +537,35 @@ class DuoSeqShardKVCache(DuoKVCache):
             scale = self.head_dim ** -0.5
         cp = cos.data_ptr() if cos is not None else None
         sp = sin.data_ptr() if sin is not None else None
-        _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode, S, stream))
         nfq = self.num_full_kv_head_list[l] * self.num_kv_groups
         po, pl = self.part_o[:, :S], self.part_lse[:, :S]
+        fused = S == 1 and qkv.stride(1) % 8 == 0 and qkv.data_ptr() % 16 == 0
+        if not fused:
+            _C.check(lib.duo_rope_append(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode, S, stream))
         if S != self.max_q:  # the kernels index [batch][q_len][heads]: contiguous views of the right q_len
             po = self.part_o.view(-1)[: B * S * self.num_heads * self.head_dim].view(B, S, self.num_heads, self.head_dim)
             pl = self.part_lse.view(-1)[: B * S * self.num_heads].view(B, S, self.num_heads)
         if self.profile_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _C.check(lib.duo_attention_seq(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), po.data_ptr(),
-                                       pl.data_ptr(), S, float(scale), self.workspace.data_ptr(),
-                                       self.workspace.numel(), stream))
+        if fused:  # one token: RoPE + owner-only append + slice attention + streaming heads + ring commit, one launch
+            _C.check(lib.duo_decode_fused_seq(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), cp, sp, rope_mode & 0xFF,
+                                              out.data_ptr(), po.data_ptr(), pl.data_ptr(), float(scale),
+                                              self.workspace.data_ptr(), self.workspace.numel(), stream))
+        else:
+            _C.check(lib.duo_attention_seq(h, C.byref(st), qkv.data_ptr(), qkv.stride(1), out.data_ptr(), po.data_ptr(),
+                                           pl.data_ptr(), S, float(scale), self.workspace.data_ptr(),
+                                           self.workspace.numel(), stream))
         if self.profile_events is not None:
             e1.record()
             self.profile_events.append((e0, e1))
         if nfq:
             self.seq.comm.merge(po, pl, out, B * S, self.num_heads, nfq)
-        _C.check(lib.duo_stream_commit(h, C.byref(st), S, stream))
-        self.launch_count += 2 + (1 if nfq else 0) + (1 if self.num_streaming_kv_head_list[l] > 0 else 0)
+        if fused:
+            self.launch_count += 1 + (1 if nfq else 0)
+        else:
+            _C.check(lib.duo_stream_commit(h, C.byref(st), S, stream))
+            self.launch_count += 2 + (1 if nfq else 0) + (1 if self.num_streaming_kv_head_list[l] > 0 else 0)
         self.advance(l, S)
         return out
 

@@ -255,6 +255,12 @@ DUO_API int duo_attention_partial(const duo_layer* layer, int64_t n_keys, const 
 DUO_API int duo_attention_seq(const duo_layer* layer, const duo_cache_state* st, const void* q, int64_t q_row_stride,
                               void* out, float* out_o, float* out_lse, int32_t q_len, float scale, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* duo_decode_fused for a sequence-sharded cache, ONE new token per batch row: RoPE + append (by the owner of the position
+ * only) + slice attention (partials as duo_attention_seq) + streaming heads + ring commit in one launch; follow with
+ * duo_seq_merge. */
+DUO_API int duo_decode_fused_seq(const duo_layer* layer, const duo_cache_state* st, const void* qkv, int64_t qkv_row_stride,
+                                 const void* cos, const void* sin, int32_t rope_mode, void* out, float* out_o,
+                                 float* out_lse, float scale, void* workspace, size_t workspace_bytes, void* stream);
 DUO_API int duo_merge_partials(const float* o_parts, const float* lse_parts, int32_t n_parts, int64_t tokens,
                                int32_t heads_total, int32_t heads_used, void* out, int32_t dtype, void* stream);
 
