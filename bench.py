@@ -85,6 +85,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fa2", action="store_true", help="skip the same-box FlashAttention-2 micro-comparison")
     ap.add_argument("--no-graph", action="store_true", help="drive decode eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the timed regions: kernel table (torch.profiler / CUPTI, rank 0) of eager decode steps -> "
+                         "gpurun_out/profile_step_n<N>.txt; never used for a bench value")
     ap.add_argument("--head-tp-decode", action="store_true",
                     help="N > 1: decode head-parallel like the reference's TP rule instead of sequence-sharded (A/B)")
     args = ap.parse_args()
@@ -515,6 +518,8 @@ def main():
             decode_step_resident()
         torch.cuda.synchronize()
     clocks = sampler.stop()
+    if args.profile_step:
+        profile_decode_steps(model, cache, tok_dev, rank, world)
     if graph is not None:  # a replayed step launches the same kernels as the captured one
         launches = args.steps * per_step_launches(cache, ops, model, tok_dev)
 
@@ -702,6 +707,35 @@ def fa2_same_box(dev, ctx, chunk, prefill_ctx):
     del cache
     torch.cuda.empty_cache()
     return res
+
+
+def profile_decode_steps(model, cache, tok_dev, rank, world, steps=3):
+    """Kernel-level table of `steps` EAGER decode steps on rank 0 (every rank runs the steps: they contain the
+    exchanges).  Evidence for which kernel / exchange limits a multi-GPU step; kept under profiles/."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+
+    ds, cache.dev_state = cache.dev_state, None
+
+    def run():
+        with torch.no_grad():
+            for _ in range(steps):
+                model(input_ids=tok_dev, past_key_values=cache, use_cache=True)
+                cache.evict_last(1)
+        torch.cuda.synchronize()
+
+    run()
+    if rank == 0:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run()
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"profile_step_n{world}.txt"), "w") as f:
+            f.write(f"{steps} eager decode steps, rank 0 of {world} (torch.profiler, CUDA activities)\n")
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=90))
+    else:
+        run()
+    cache.dev_state = ds
+    cache.sync_device_state()
 
 
 def per_step_launches(cache, ops, model, tok_dev):
