@@ -85,6 +85,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fa2", action="store_true", help="skip the same-box FlashAttention-2 micro-comparison")
     ap.add_argument("--no-graph", action="store_true", help="drive decode eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--prefill-only", action="store_true", help="tuning: stop after the prefill (+ reshard) measurement")
+    ap.add_argument("--tp-pipeline-blocks", type=int, default=None,
+                    help="N > 1 prefill: row blocks of the pipelined all-reduce (0 = plain NCCL all-reduce per site)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the timed regions: kernel table (torch.profiler / CUPTI, rank 0) of eager decode steps -> "
                          "gpurun_out/profile_step_n<N>.txt; never used for a bench value")
@@ -341,6 +344,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        # NCCL kernels on a high-priority stream: the prefill overlaps its 256 MiB all-reduces with GEMMs that would
+        # otherwise keep every SM busy until they drain
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     from duo_attention_b200 import _C, ops
@@ -350,6 +356,10 @@ def main():
     mask, sparsity = head_pattern(args.pattern, args.sparsity)
     mask = mask[: args.layers]
     model, local_mask, head_plan = build_model(args, mask, rank, world, dev)
+    if args.tp_pipeline_blocks is not None:
+        model._duo_tp_pipeline_blocks = max(1, args.tp_pipeline_blocks)
+        if args.tp_pipeline_blocks == 0:
+            model._duo_tp_pipeline_rows = 1 << 60
     vocab = {**L3_8B, **ARCHS[args.arch][0]}["vocab_size"]
 
     def barrier():
@@ -432,15 +442,26 @@ def main():
         from duo_attention_b200.kv_cache import DuoSeqShardKVCache
 
         model_sp, decode_mask, _ = build_model(args, mask, rank, world, dev, seq_shard=True)
-        cache_sp = DuoSeqShardKVCache(model_sp, decode_mask, 1, args.ctx + 8, SINK, RECENT)
+        cache_sp = DuoSeqShardKVCache(model_sp, decode_mask, 1, (args.prefill_ctx if args.prefill_only else args.ctx) + 8,
+                                      SINK, RECENT)
         if not args.no_prefill:
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            cache_sp.load_from_head_parallel(cache, head_plan)
-            e1.record()
-            barrier()
-            result["prefill"]["reshard_to_sequence_sharded_ms"] = max_over_ranks(e0.elapsed_time(e1))
+            for key in ("reshard_first_call_ms", "reshard_to_sequence_sharded_ms"):
+                # first call: includes NCCL's lazy point-to-point connection set-up between every pair of ranks
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                cache_sp.load_from_head_parallel(cache, head_plan)
+                e1.record()
+                barrier()
+                result["prefill"][key] = max_over_ranks(e0.elapsed_time(e1))
+        if args.prefill_only:
+            if rank == 0:
+                print(json.dumps({"prefill_only": True, "n_gpus": world, "tp_pipeline_blocks": args.tp_pipeline_blocks,
+                                  **result}), flush=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         del cache, model
         torch.cuda.empty_cache()
         model, cache = model_sp, cache_sp
