@@ -226,7 +226,7 @@ def duo_causal_lm_forward(self, input_ids: Optional[torch.LongTensor] = None, at
             if pipelined and idx + 1 < len(layers):
                 ctx = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx, rope_mode, project=False)
                 x = _tp_layer_pipelined(layer, ctx, h, layers[idx + 1].input_layernorm, self._duo_tp_group,
-                                        getattr(self, "_duo_tp_pipeline_blocks", 4))
+                                        getattr(self, "_duo_tp_pipeline_blocks", 2))
                 continue
             a = duo_attention_layer_forward(layer.self_attn, x, cos, sin, cache, idx, rope_mode)
             ln2 = layer.post_attention_layernorm
