@@ -210,6 +210,28 @@ def streaming_visible(t, j, cs, sink, recent):
     return j < sink or j >= cs - recent
 
 
+def training_streaming_mask(seq_len, sink, recent):
+    """Training-time streaming (Lambda) mask, True = visible (duo_attn/patch/streaming_attn.py:14-24): query t sees key j
+    iff ``j <= t and (j < sink or j > t - recent)`` — the window INCLUDES the query itself, so it holds ``recent`` keys
+    where the deploy-time decode step sees ``recent + 1`` (ring + the new token).  Padded to a multiple of 8 like the
+    reference."""
+    n = (seq_len + 7) // 8 * 8
+    t = torch.arange(n)[:, None]
+    j = torch.arange(n)[None, :]
+    return (j <= t) & ((j < sink) | (j > t - recent))
+
+
+def training_streaming_attention(q, k, v, sink, recent):
+    """Whole-sequence streaming attention under the training-time mask (streaming_attn.py:27-42: SDPA with the boolean
+    mask, GQA by head repetition, scale 1/sqrt(D)).  q ``[B,S,Hq,D]``, k/v ``[B,S,Hkv,D]``; fp32 math."""
+    B, S, Hq, D = q.shape
+    g = Hq // k.shape[2]
+    mask = training_streaming_mask(S, sink, recent)[:S, :S]
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float().repeat_interleave(g, dim=2)) / math.sqrt(D)
+    s = s.masked_fill(~mask[None, None], float("-inf"))
+    return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v.float().repeat_interleave(g, dim=2))
+
+
 # --------------------------------------------------------------------------------------
 # Attention-layer oracle, tuple cache  (llama.py:146-306)
 # --------------------------------------------------------------------------------------

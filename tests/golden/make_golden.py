@@ -267,9 +267,33 @@ def make_int4_fixtures(O, GC):
     print("wrote w8a8kv4_enable (sink/recent attrs:", layers[0].self_attn.sink_size, layers[0].self_attn.recent_size, ")")
 
 
+def make_training_mask_fixtures(GC):
+    """The reference's training-time streaming mask and its SDPA streaming attention, run unmodified on the CPU
+    (duo_attn/patch/streaming_attn.py:14-42; the module imports without its optional CUDA packages)."""
+    sys.path.insert(0, REF)
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_streaming_attn", os.path.join(REF, "duo_attn/patch/streaming_attn.py"))
+    sa = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sa)
+    out = {}
+    for case in GC.TRAIN_MASK_CASES:
+        q, k, v = GC.make_train_mask_inputs(case)
+        mask = sa.generate_streaming_mask(case["S"], case["sink"], case["recent"], "cpu")
+        o = sa.streaming_attn_sdpa(q, k, v, mask)
+        out[f"mask_{case['name']}"] = mask[0, 0].numpy()
+        out[f"out_{case['name']}"] = o.numpy().astype(np.float32)
+        out[f"checksum_{case['name']}"] = np.float64(sum(float(t.double().abs().sum()) for t in (q, k, v)))
+    np.savez_compressed(os.path.join(HERE, "training_masks.npz"), **out)
+    print("wrote training masks", len(GC.TRAIN_MASK_CASES))
+
+
 def main():
     from oracle import duo_oracle as O
     import golden_cases as GC
+
+    if sys.argv[1:] == ["masks"]:
+        return make_training_mask_fixtures(GC)
 
     ref_llama, ref_mistral, ref_putils, ref_utils = import_reference()
     assert ref_llama.__file__.startswith(REF), ref_llama.__file__
@@ -367,6 +391,9 @@ def main():
 
     # ---------------------------------------------------------------- INT4-KV fixtures
     make_int4_fixtures(O, GC)
+
+    # ---------------------------------------------------------------- training-time streaming masks
+    make_training_mask_fixtures(GC)
 
     # ---------------------------------------------------------------- reorder fixtures
     for case in GC.REORDER_CASES:

@@ -42,6 +42,23 @@ INT4_CASES = [
          max_size=32, prefill_chunk=32),
 ]
 
+# Training-time streaming (Lambda) masks: generate_streaming_mask + streaming_attn_sdpa (duo_attn/patch/streaming_attn.py:14-42)
+TRAIN_MASK_CASES = [
+    dict(name="s37_4_8", S=37, Hq=4, Hkv=2, sink=4, recent=8, seed=51),
+    dict(name="s64_16_16", S=64, Hq=4, Hkv=4, sink=16, recent=16, seed=52),
+    dict(name="s24_0_5", S=24, Hq=2, Hkv=1, sink=0, recent=5, seed=53),
+    dict(name="s20_3_1", S=20, Hq=2, Hkv=2, sink=3, recent=1, seed=54),
+    dict(name="s330_64_257", S=330, Hq=2, Hkv=1, sink=64, recent=257, seed=55),  # deploy 64/256 in the chunk-1 limit (+1)
+]
+
+
+def make_train_mask_inputs(case):
+    g = torch.Generator().manual_seed(case["seed"])
+    q = torch.randn(1, case["S"], case["Hq"], D, generator=g)
+    k = torch.randn(1, case["S"], case["Hkv"], D, generator=g)
+    v = torch.randn(1, case["S"], case["Hkv"], D, generator=g)
+    return q, k, v
+
 
 def make_int4_inputs(case):
     """Post-RoPE fp16 q/k/v per chunk (RoPE is pinned separately; the fixture isolates cache + attention)."""

@@ -160,3 +160,41 @@ def test_oracle_model_matches_reference_patched_model(case):
     # the schedule really exercised the streaming window (the cache was compacted at least once)
     if case["path"] == "static" and past[0][1].shape[1]:
         assert int(fx["lens"][:, 1].max()) <= case["sink"] + case["recent"] < int(fx["lens"][:, 0].max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Training-time streaming (Lambda) mask: reference generate_streaming_mask / streaming_attn_sdpa run on the CPU
+# (duo_attn/patch/streaming_attn.py:14-42) -> tests/golden/training_masks.npz.  SURVEY 8c item 3.
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("case", GC.TRAIN_MASK_CASES, ids=lambda c: c["name"])
+def test_training_mask_closed_form_matches_reference_mask(case):
+    f = np.load(os.path.join(GOLD, "training_masks.npz"))
+    q, k, v = GC.make_train_mask_inputs(case)
+    assert abs(float(f[f"checksum_{case['name']}"]) - sum(float(t.double().abs().sum()) for t in (q, k, v))) < 1e-6
+    ref_mask = torch.from_numpy(f[f"mask_{case['name']}"])
+    assert torch.equal(O.training_streaming_mask(case["S"], case["sink"], case["recent"]), ref_mask)
+    out = O.training_streaming_attention(q, k, v, case["sink"], case["recent"])
+    torch.testing.assert_close(out, torch.from_numpy(f[f"out_{case['name']}"]), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [c for c in GC.TRAIN_MASK_CASES if c["recent"] >= 2], ids=lambda c: c["name"])
+def test_deploy_decode_equals_training_mask_with_recent_plus_one(case):
+    """The chunk = 1 limit of the deploy-time path (prefill of one token, then token-by-token decode through the tuple
+    cache) is the training-time mask with ``recent + 1``: the decode step sees the ring (``recent`` keys) plus the new
+    token, the training mask counts the query itself inside its window.  Held against the REFERENCE's mask + SDPA."""
+    f = np.load(os.path.join(GOLD, "training_masks.npz"))
+    q, k, v = GC.make_train_mask_inputs(case)
+    groups = case["Hq"] // case["Hkv"]
+    outs, past = [], None
+    for t in range(case["S"]):
+        o, past = O.tuple_attention_core(q[:, t:t + 1], k[:, t:t + 1], v[:, t:t + 1], past, 0, groups, case["sink"],
+                                         case["recent"] - 1)
+        outs.append(o.float())
+    torch.testing.assert_close(torch.cat(outs, dim=1), torch.from_numpy(f[f"out_{case['name']}"]), rtol=1e-4, atol=1e-5)
+    # and cell by cell: closed-form deploy visibility (chunk start = the token itself) == the reference's mask
+    ref_mask = f[f"mask_{case['name']}"]
+    for t in range(case["S"]):
+        for j in range(case["S"]):
+            assert O.streaming_visible(t, j, t, case["sink"], case["recent"] - 1) == bool(ref_mask[t, j]), (t, j)
