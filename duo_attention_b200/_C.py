@@ -17,6 +17,7 @@ KV_SAME, KV_INT4 = 0, 1
 ROPE_NONE, ROPE_HF, ROPE_FP32 = 0, 1, 2
 ROPE_SKIP_Q = 0x100
 DECODE_MAX_Q = 16
+DECODE_MAX_Q_INT4 = 8  # packed rows (group x q_len) of duo_decode_fused on an INT4 cache
 
 # every symbol include/duo_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [

@@ -64,6 +64,9 @@ int launch_attn_mma_seq(const duo_layer* L, const duo_cache_state* st, const voi
 int launch_decode_fused(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
                         const void* cos, const void* sin, int rope_mode, void* out, int q_len, float scale,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_decode_fused_int4(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
+                             const void* cos, const void* sin, int rope_mode, void* out, int q_len, float scale,
+                             void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_decode_fused_seq(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
                             const void* cos, const void* sin, int rope_mode, void* out, float* part_o, float* part_lse,
                             float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -298,8 +301,9 @@ int duo_decode_fused(const duo_layer* layer, const duo_cache_state* st, const vo
     set_error("duo_decode_fused: bad rope_mode %d", rope_mode);
     return DUO_EINVAL;
   }
-  if (layer->d.kv_format != DUO_KV_SAME || layer->d.group * q_len > 16 || st->seq_world != 0) {
-    set_error("duo_decode_fused: 16-bit unsharded caches and group * q_len <= 16 only (got group %d, q_len %d)",
+  const int max_rows = layer->d.kv_format == DUO_KV_INT4 ? DUO_DECODE_MAX_Q_INT4 : DUO_DECODE_MAX_Q;
+  if (layer->d.group * q_len > max_rows || st->seq_world != 0) {
+    set_error("duo_decode_fused: unsharded caches and group * q_len <= %d only (got group %d, q_len %d)", max_rows,
               layer->d.group, q_len);
     return DUO_EINVAL;
   }
@@ -307,6 +311,9 @@ int duo_decode_fused(const duo_layer* layer, const duo_cache_state* st, const vo
     set_error("duo_decode_fused: qkv rows must be 16-byte aligned (row stride a multiple of 8 elements)");
     return DUO_EINVAL;
   }
+  if (layer->d.kv_format == DUO_KV_INT4)
+    return launch_decode_fused_int4(layer, st, qkv, qkv_row_stride, cos, sin, rope_mode, out, q_len, scale, workspace,
+                                    workspace_bytes, (cudaStream_t)stream);
   return launch_decode_fused(layer, st, qkv, qkv_row_stride, cos, sin, rope_mode, out, q_len, scale, workspace,
                              workspace_bytes, (cudaStream_t)stream);
 }

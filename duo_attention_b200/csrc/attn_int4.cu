@@ -53,6 +53,12 @@ struct I4Params {
   SplitWs ws;  // split-KV partials + arrival counters (duo_common.cuh)
   const uint8_t *full_k, *full_v, *ring_k, *ring_v;
   const __half *fks, *fkz, *fvs, *fvz, *rks, *rkz, *rvs, *rvz;
+  // FUSED decode step (duo_decode_fused on an INT4 cache, duo_attn_int4_dec8_kernel<true>): `q` points at the RAW fused
+  // qkv rows; the kernel rotates q in registers, and the CTA that owns the end of a head's key range rotates the new
+  // tokens' K, quantises K / V (K1) into the cache rows the loop then reads, and commits the streaming ring at the end.
+  const void *cos, *sin;
+  int rope_mode;
+  long long k_off, v_off;  // element offsets of the k / v sections inside a qkv row
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -566,6 +572,7 @@ __device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
   return d;
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const I4Params pin) {
   DUO_TRACE_STAMP(0);
   I4Params p = pin;
@@ -686,8 +693,46 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     }
     cp_async_commit();
   };
+  // FUSED: the new tokens — RoPE(K) and K1 quantisation of K and V into the rows this CTA is about to read (retrieval
+  // heads: cache rows full_len + t, written by the split whose key range holds them; streaming heads: the staging rows).
+  auto append_new = [&]() {
+    // one warp per (token, K|V) row, arithmetic of rope_append_kernel (kv_ops.cu) => the same bits as the unfused path
+    const __half* rows = reinterpret_cast<const __half*>(p.q) + (long long)b * p.q_batch_stride;
+    for (int w = warp; w < 2 * p.q_len; w += I4_THREADS / 32) {
+      const int t = w >> 1;
+      const bool is_k = (w & 1) == 0;
+      long long dr;  // destination row inside this head's cache
+      if (is_full) {
+        dr = p.full_len + t;
+        if (dr < a0 || dr >= a1) continue;  // another split owns (and reads) this row
+      } else {
+        dr = (long long)p.stage_off + t;
+      }
+      const __half* src = rows + (long long)t * p.q_tok_stride + (is_k ? p.k_off : p.v_off) + (long long)kvh * kHeadDim;
+      Vec4<__half> xv = *reinterpret_cast<const Vec4<__half>*>(src + lane * 4);
+      if (is_k && p.rope_mode != DUO_ROPE_NONE) rope_row4<__half>(xv, lane, t, p.cos, p.sin, p.rope_mode);
+      float xo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xo[i] = __half2float(xv.v[i]);
+      quant_row_int4(xo, lane, const_cast<uint8_t*>(is_k ? gk : gv) + dr * 64,
+                     const_cast<__half*>(is_k ? gks : gvs) + dr, const_cast<__half*>(is_k ? gkz : gvz) + dr);
+    }
+    __threadfence();
+    __syncthreads();  // the rows are in memory before any cp.async of this CTA may fetch them
+  };
+  // The first STAGES - 1 tiles are fetched before the new rows are produced (their loads fly meanwhile) unless one of
+  // them already holds a new row (short key ranges).
+  bool append_first = false;
+  if constexpr (FUSED)
+    append_first = is_full ? (a0 + (long long)(D8_STAGES - 1) * D8_TILE > p.full_len) : (nA < D8_STAGES - 1);
+  if constexpr (FUSED) {
+    if (append_first) append_new();
+  }
 #pragma unroll
   for (int i = 0; i < D8_STAGES - 1; ++i) issue(i);
+  if constexpr (FUSED) {
+    if (!append_first) append_new();
+  }
 
   // ---- Q^T as B fragments: lane (g, t4) holds query row g, head_dim chunk 32 t4 .. 32 t4 + 31 ------------
   const int wkey = warp * KPW;
@@ -706,6 +751,18 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
       __half e[8];
       if (ok) {
         *reinterpret_cast<uint4*>(e) = *reinterpret_cast<const uint4*>(src + 8 * w);
+        if constexpr (FUSED) {
+          if (p.rope_mode != DUO_ROPE_NONE) {  // partner of head_dim d is d +- 64: the chunk of lane t4 ^ 2
+            uint4 mine = *reinterpret_cast<const uint4*>(e);
+            uint4 other = *reinterpret_cast<const uint4*>(src + 8 * w + (t4 < 2 ? 64 : -64));
+            if (t4 < 2) {
+              rope8<__half>(mine, other, p.cos, p.sin, p.rope_mode, tok, 32 * t4 + 8 * w);
+            } else {
+              rope8<__half>(other, mine, p.cos, p.sin, p.rope_mode, tok, 32 * (t4 - 2) + 8 * w);
+            }
+            *reinterpret_cast<uint4*>(e) = mine;
+          }
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] = __float2half(0.f);
@@ -950,6 +1007,29 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
     *reinterpret_cast<uint32_t*>(dst) = Op::pack(v0, v1);
   };
   const int nsplit = is_full ? p.splits_full : 1;
+  if constexpr (FUSED) {
+    if (!is_full) {
+      // ---- ring commit (stream_commit_kernel): this CTA was the only reader of the head's ring and has drained its
+      // pipeline, so the staged rows of the new tokens may now overwrite their sink / ring slots ----
+      for (int w = warp; w < 2 * p.q_len; w += I4_THREADS / 32) {
+        const int t = w >> 1;
+        const long long pos = p.total + t;
+        long long slot;
+        if (pos < p.sink) slot = pos;
+        else if (t >= p.q_len - p.recent) slot = p.sink + (pos - p.sink) % p.recent;
+        else continue;
+        const long long srow = (long long)p.stage_off + t;
+        uint8_t* base = const_cast<uint8_t*>((w & 1) ? gv : gk);
+        *reinterpret_cast<uint16_t*>(base + slot * 64 + lane * 2) = *reinterpret_cast<const uint16_t*>(base + srow * 64 + lane * 2);
+        if (lane == 0) {
+          __half* sc = const_cast<__half*>((w & 1) ? gvs : gks);
+          __half* zp = const_cast<__half*>((w & 1) ? gvz : gkz);
+          sc[slot] = sc[srow];
+          zp[slot] = zp[srow];
+        }
+      }
+    }
+  }
   if (nsplit == 1) {
     for (int idx = tid; idx < rows_total * 64; idx += I4_THREADS) {
       const int r = idx >> 6, d = (idx & 63) * 2;
@@ -1065,11 +1145,23 @@ static int launch_i4(const duo_layer* L, const duo_cache_state* st, const void* 
 }
 
 // Launch of duo_attn_int4_dec8_kernel (group * q_len <= 8): 4 CTAs / SM, 8-row split-KV workspace.
+struct FusedI4Args {  // duo_decode_fused on an INT4 cache: q points at the raw qkv rows
+  const void *cos, *sin;
+  int rope_mode;
+};
+
 static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const void* q, long long q_row_stride,
                           void* out, int q_len, float scale, void* workspace, size_t workspace_bytes,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const FusedI4Args* fused = nullptr) {
   const duo_layer_desc& d = L->d;
   I4Params p{};
+  if (fused) {
+    p.cos = fused->cos;
+    p.sin = fused->sin;
+    p.rope_mode = fused->rope_mode;
+    p.k_off = (long long)(d.n_full + d.n_stream) * d.group * kHeadDim;
+    p.v_off = p.k_off + (long long)(d.n_full + d.n_stream) * kHeadDim;
+  }
   p.q = q;
   p.out = out;
   p.q_tok_stride = q_row_stride;
@@ -1139,11 +1231,28 @@ static int launch_i4_dec8(const duo_layer* L, const duo_cache_state* st, const v
   }
   const int grid_x = d.n_full * splits + d.n_stream;
   if (grid_x == 0) return DUO_OK;
-  static unsigned long long attr_mask = 0;  // four CTAs of 51 KB per SM: also ask for the full smem carve-out
-  if (int rc = ensure_dyn_smem(duo_attn_int4_dec8_kernel, D8_SMEM_BYTES, &attr_mask, true)) return rc;
-  duo_attn_int4_dec8_kernel<<<dim3(grid_x, d.batch), I4_THREADS, D8_SMEM_BYTES, stream>>>(p);
+  // four CTAs of 51 KB per SM: also ask for the full smem carve-out
+  if (fused) {
+    static unsigned long long attr_mask = 0;
+    if (int rc = ensure_dyn_smem(duo_attn_int4_dec8_kernel<true>, D8_SMEM_BYTES, &attr_mask, true)) return rc;
+    duo_attn_int4_dec8_kernel<true><<<dim3(grid_x, d.batch), I4_THREADS, D8_SMEM_BYTES, stream>>>(p);
+  } else {
+    static unsigned long long attr_mask = 0;
+    if (int rc = ensure_dyn_smem(duo_attn_int4_dec8_kernel<false>, D8_SMEM_BYTES, &attr_mask, true)) return rc;
+    duo_attn_int4_dec8_kernel<false><<<dim3(grid_x, d.batch), I4_THREADS, D8_SMEM_BYTES, stream>>>(p);
+  }
   DUO_CUDA_TRY(cudaGetLastError());
   return DUO_OK;
+}
+
+// One decode-sized chunk over an INT4 cache, everything in one launch (duo_decode_fused): RoPE(q, k) + K1 quantisation
+// and append of the new K / V + mixed-head attention + ring commit.  `qkv` is the raw fused projection output; it is
+// NOT modified.  group * q_len <= 8 (the keys-as-M kernel).
+int launch_decode_fused_int4(const duo_layer* L, const duo_cache_state* st, const void* qkv, long long row_stride,
+                             const void* cos, const void* sin, int rope_mode, void* out, int q_len, float scale,
+                             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const FusedI4Args fa{cos, sin, rope_mode};
+  return launch_i4_dec8(L, st, qkv, row_stride, out, q_len, scale, workspace, workspace_bytes, stream, &fa);
 }
 
 #ifdef DUO_TRACE

@@ -68,31 +68,7 @@ struct AttnParams {
   int ring_slots;
 };
 
-// RoPE of 8 consecutive head_dim elements d .. d+7 (d < 64) and their partners d+64 .. d+71, arithmetic of
-// rope_append_kernel (kv_ops.cu): HF mode rounds every product and the sum to T, fp32 mode rounds once.
-template <typename T>
-__device__ __forceinline__ void rope8(uint4& lo, uint4& hi, const void* cos, const void* sin, int mode, int tok, int d) {
-  T* xl = reinterpret_cast<T*>(&lo);
-  T* xh = reinterpret_cast<T*>(&hi);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float a = RopeCvt<T>::to_f(xl[e]), bb = RopeCvt<T>::to_f(xh[e]);
-    float ol, oh;
-    if (mode == DUO_ROPE_HF) {
-      const T* ct = reinterpret_cast<const T*>(cos) + (long long)tok * kHeadDim;
-      const T* st = reinterpret_cast<const T*>(sin) + (long long)tok * kHeadDim;
-      ol = rope_hf<T>(a, -bb, RopeCvt<T>::to_f(ct[d + e]), RopeCvt<T>::to_f(st[d + e]));
-      oh = rope_hf<T>(bb, a, RopeCvt<T>::to_f(ct[d + 64 + e]), RopeCvt<T>::to_f(st[d + 64 + e]));
-    } else {
-      const float* ct = reinterpret_cast<const float*>(cos) + (long long)tok * kHeadDim;
-      const float* st = reinterpret_cast<const float*>(sin) + (long long)tok * kHeadDim;
-      ol = rope_f32(a, -bb, ct[d + e], st[d + e]);
-      oh = rope_f32(bb, a, ct[d + 64 + e], st[d + 64 + e]);
-    }
-    xl[e] = RopeCvt<T>::from_f(ol);
-    xh[e] = RopeCvt<T>::from_f(oh);
-  }
-}
+// rope8<T> (RoPE of 8 head_dim elements and their +64 partners): duo_common.cuh
 
 // rows of the block-cyclic slice of `rank` that hold positions < n  (host twin: seqshard.SeqShardPlan.local_len)
 __host__ __device__ __forceinline__ long long seq_local_len(long long n, int rank, int world, int block) {

@@ -193,6 +193,107 @@ __device__ __forceinline__ float rope_f32(float x, float rot, float c, float s) 
   return __fmaf_rn(rot, s, __fmul_rn(x, c));
 }
 
+// RoPE of 8 consecutive head_dim elements d .. d+7 (d < 64) and their partners d+64 .. d+71, arithmetic of
+// rope_append_kernel (kv_ops.cu): HF mode rounds every product and the sum to T, fp32 mode rounds once.
+template <typename T>
+__device__ __forceinline__ void rope8(uint4& lo, uint4& hi, const void* cos, const void* sin, int mode, int tok, int d) {
+  T* xl = reinterpret_cast<T*>(&lo);
+  T* xh = reinterpret_cast<T*>(&hi);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float a = RopeCvt<T>::to_f(xl[e]), bb = RopeCvt<T>::to_f(xh[e]);
+    float ol, oh;
+    if (mode == DUO_ROPE_HF) {
+      const T* ct = reinterpret_cast<const T*>(cos) + (long long)tok * kHeadDim;
+      const T* st = reinterpret_cast<const T*>(sin) + (long long)tok * kHeadDim;
+      ol = rope_hf<T>(a, -bb, RopeCvt<T>::to_f(ct[d + e]), RopeCvt<T>::to_f(st[d + e]));
+      oh = rope_hf<T>(bb, a, RopeCvt<T>::to_f(ct[d + 64 + e]), RopeCvt<T>::to_f(st[d + 64 + e]));
+    } else {
+      const float* ct = reinterpret_cast<const float*>(cos) + (long long)tok * kHeadDim;
+      const float* st = reinterpret_cast<const float*>(sin) + (long long)tok * kHeadDim;
+      ol = rope_f32(a, -bb, ct[d + e], st[d + e]);
+      oh = rope_f32(bb, a, ct[d + 64 + e], st[d + 64 + e]);
+    }
+    xl[e] = RopeCvt<T>::from_f(ol);
+    xh[e] = RopeCvt<T>::from_f(oh);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One 128-element row held 4-per-lane by a warp (lane l: elements 4l .. 4l+3): RoPE and INT4 K1 quantisation.
+// Shared by rope_append_kernel (kv_ops.cu) and the fused INT4 decode kernel (attn_int4.cu): same bits from both.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct alignas(8) Vec4 {
+  T v[4];
+};
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// RoPE of token `t` (row t of the cos / sin tables of this chunk) on a warp-held row; every lane must call.
+template <typename T>
+__device__ __forceinline__ void rope_row4(Vec4<T>& xv, int lane, int t, const void* cos, const void* sin, int mode) {
+  // rotate_half partner: element i pairs with i +- 64  <=> lane +- 16
+  Vec4<T> pv;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float mine = RopeCvt<T>::to_f(xv.v[i]);
+    const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+    pv.v[i] = RopeCvt<T>::from_f(lane < 16 ? -other : other);
+  }
+  if (mode == DUO_ROPE_HF) {
+    const Vec4<T> cv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(cos) + (long long)t * kHeadDim + lane * 4);
+    const Vec4<T> sv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(sin) + (long long)t * kHeadDim + lane * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      xv.v[i] = RopeCvt<T>::from_f(rope_hf<T>(RopeCvt<T>::to_f(xv.v[i]), RopeCvt<T>::to_f(pv.v[i]), RopeCvt<T>::to_f(cv.v[i]),
+                                              RopeCvt<T>::to_f(sv.v[i])));
+  } else {
+    const float4 cv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(cos) + (long long)t * kHeadDim + lane * 4);
+    const float4 sv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sin) + (long long)t * kHeadDim + lane * 4);
+    const float c[4] = {cv.x, cv.y, cv.z, cv.w};
+    const float s[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      xv.v[i] = RopeCvt<T>::from_f(rope_f32(RopeCvt<T>::to_f(xv.v[i]), RopeCvt<T>::to_f(pv.v[i]), c[i], s[i]));
+  }
+}
+
+// K1 arithmetic (demo/quantize_int4.cu:73-144) for one 128-element group held 4-per-lane (fp16-representable values
+// in x[]).  Writes 2 packed bytes per lane; lane 0 writes scale / zero.
+__device__ __forceinline__ void quant_row_int4(const float (&x)[4], int lane, uint8_t* packed_row, __half* scale_p,
+                                               __half* zero_p) {
+  float mn = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
+  float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  const float scale = __fadd_rn(__fdiv_rn(__fsub_rn(mx, mn), 15.0f), 1e-8f);
+  const float zero = mn;
+  uint32_t q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float qf = __fdiv_rn(__fsub_rn(x[i], zero), scale);
+    qf = roundf(qf);
+    qf = fminf(fmaxf(qf, 0.0f), 15.0f);
+    q[i] = (uint32_t)qf;
+  }
+  const uint16_t two = (uint16_t)(((q[0] << 4) | q[1]) | (((q[2] << 4) | q[3]) << 8));
+  *reinterpret_cast<uint16_t*>(packed_row + 2 * lane) = two;
+  if (lane == 0) {
+    *scale_p = __float2half_rn(scale);
+    *zero_p = __float2half_rn(zero);
+  }
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

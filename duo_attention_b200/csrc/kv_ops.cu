@@ -15,61 +15,6 @@ namespace duo {
 
 int stage_offset(const duo_layer_desc& d);  // api.cu
 
-template <typename T>
-struct Cvt;
-template <>
-struct Cvt<__nv_bfloat16> {
-  __device__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
-  __device__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
-};
-template <>
-struct Cvt<__half> {
-  __device__ static float to_f(__half v) { return __half2float(v); }
-  __device__ static __half from_f(float v) { return __float2half_rn(v); }
-};
-
-template <typename T>
-struct alignas(8) Vec4 {
-  T v[4];
-};
-
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// K1 arithmetic for one 128-element group held 4-per-lane (fp16-representable values in x[]).
-// Writes 2 packed bytes per lane; lane 0 writes scale / zero.
-__device__ __forceinline__ void quant_row_int4(const float (&x)[4], int lane, uint8_t* packed_row, __half* scale_p,
-                                               __half* zero_p) {
-  float mn = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
-  float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
-  mn = warp_min(mn);
-  mx = warp_max(mx);
-  const float scale = __fadd_rn(__fdiv_rn(__fsub_rn(mx, mn), 15.0f), 1e-8f);
-  const float zero = mn;
-  uint32_t q[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float qf = __fdiv_rn(__fsub_rn(x[i], zero), scale);
-    qf = roundf(qf);
-    qf = fminf(fmaxf(qf, 0.0f), 15.0f);
-    q[i] = (uint32_t)qf;
-  }
-  const uint16_t two = (uint16_t)(((q[0] << 4) | q[1]) | (((q[2] << 4) | q[3]) << 8));
-  *reinterpret_cast<uint16_t*>(packed_row + 2 * lane) = two;
-  if (lane == 0) {
-    *scale_p = __float2half_rn(scale);
-    *zero_p = __float2half_rn(zero);
-  }
-}
-
 struct RopeAppendParams {
   void* qkv;
   long long row_stride;  // elements between consecutive tokens
@@ -106,34 +51,9 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const RopeAppendParams
   const bool is_v = !is_q && !is_k;
 
   float xo[4];  // values as they will be stored (already rounded to T)
-  if (!is_v && p.rope_mode != DUO_ROPE_NONE) {
-    // rotate_half partner: element i pairs with i +- 64  <=> lane +- 16
-    Vec4<T> pv;
+  if (!is_v && p.rope_mode != DUO_ROPE_NONE) rope_row4<T>(xv, lane, t, p.cos, p.sin, p.rope_mode);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float mine = Cvt<T>::to_f(xv.v[i]);
-      const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
-      pv.v[i] = Cvt<T>::from_f(lane < 16 ? -other : other);
-    }
-    if (p.rope_mode == DUO_ROPE_HF) {
-      const Vec4<T> cv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(p.cos) + (long long)t * kHeadDim + lane * 4);
-      const Vec4<T> sv = *reinterpret_cast<const Vec4<T>*>(reinterpret_cast<const T*>(p.sin) + (long long)t * kHeadDim + lane * 4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        xv.v[i] = Cvt<T>::from_f(rope_hf<T>(Cvt<T>::to_f(xv.v[i]), Cvt<T>::to_f(pv.v[i]), Cvt<T>::to_f(cv.v[i]),
-                                            Cvt<T>::to_f(sv.v[i])));
-    } else {
-      const float4 cv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.cos) + (long long)t * kHeadDim + lane * 4);
-      const float4 sv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.sin) + (long long)t * kHeadDim + lane * 4);
-      const float c[4] = {cv.x, cv.y, cv.z, cv.w};
-      const float s[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        xv.v[i] = Cvt<T>::from_f(rope_f32(Cvt<T>::to_f(xv.v[i]), Cvt<T>::to_f(pv.v[i]), c[i], s[i]));
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) xo[i] = Cvt<T>::to_f(xv.v[i]);
+  for (int i = 0; i < 4; ++i) xo[i] = RopeCvt<T>::to_f(xv.v[i]);
 
   if (is_q) {
     if (p.rope_mode != DUO_ROPE_NONE && !p.skip_q) *reinterpret_cast<Vec4<T>*>(row + lane * 4) = xv;

@@ -385,11 +385,13 @@ class DuoKVCache:
         return tot
 
     # ------------------------------------------------------------------------------------------
-    def attend(self, l, qkv, cos, sin, rope_mode, out, scale=None, force_mma=False):
+    def attend(self, l, qkv, cos, sin, rope_mode, out, scale=None, force_mma=False, fused=True):
         """The fused per-layer hot path: RoPE + append, mixed-head attention, ring commit.
 
-        qkv  ``[B, S, (Hq + 2 Hkv) * D]`` (last dim contiguous) — q is rotated in place.
+        qkv  ``[B, S, (Hq + 2 Hkv) * D]`` (last dim contiguous) — q is rotated in place on the three-launch path,
+             left untouched on the one-launch path.
         out  ``[B, S, Hq, D]`` contiguous, written.
+        ``fused=False`` forces the three-launch path for decode-sized chunks (tests: both paths produce the same bits).
         """
         if not qkv.is_cuda or not out.is_cuda:
             raise RuntimeError("duo_attention_b200 kernels need CUDA tensors (no CPU fallback)")
@@ -406,8 +408,11 @@ class DuoKVCache:
             scale = self.head_dim ** -0.5
         cp = cos.data_ptr() if cos is not None else None
         sp = sin.data_ptr() if sin is not None else None
-        if (self.kv_format == "same" and S * self.num_kv_groups <= _C.DECODE_MAX_Q and not force_mma
-                and qkv.stride(1) % 8 == 0 and qkv.data_ptr() % 16 == 0):
+        # decode-sized chunks take ONE launch: 16-bit caches up to 16 packed rows, INT4 caches up to 8 (the keys-as-M
+        # kernel) — except the very first INT4 call, which attends the raw fp16 K/V (see below)
+        one_launch = (S * self.num_kv_groups <= _C.DECODE_MAX_Q if self.kv_format == "same" else
+                      S * self.num_kv_groups <= _C.DECODE_MAX_Q_INT4 and not (st.full_len == 0 and st.total == 0))
+        if (one_launch and fused and not force_mma and qkv.stride(1) % 8 == 0 and qkv.data_ptr() % 16 == 0):
             # decode-sized chunk: RoPE + append + attention + ring commit in ONE launch (q is not written back)
             if self.profile_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

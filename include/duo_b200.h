@@ -178,14 +178,22 @@ DUO_API int duo_attention(const duo_layer* layer, const duo_cache_state* st, con
                   void* stream);
 
 /*
- * One launch for a whole decode-sized chunk (group * q_len <= 16, 16-bit caches): duo_rope_append + duo_attention +
+ * One launch for a whole decode-sized chunk (group * q_len <= 16): duo_rope_append + duo_attention +
  * duo_stream_commit fused — RoPE of q in registers, RoPE(k) / v of the new tokens written straight to their final
  * cache rows (retrieval: full_len + t; streaming: sink / ring slot, no staging round trip) and attended from a tile
  * built in shared memory.  Replaces, per decoder layer and decode step, what the reference does in
  * duo_attn/patch/llama.py:347-362 (RoPE), :353-362 + static_kv_cache.py:109-125 (append), :364-421 (attention) and
  * :423-425 + static_kv_cache.py:127-167 (streaming compaction).  `qkv` as for duo_rope_append but NOT modified;
  * cos / sin / rope_mode as for duo_rope_append (no DUO_ROPE_SKIP_Q); rows must be 16-byte aligned.
+ * INT4 caches (group * q_len <= DUO_DECODE_MAX_Q_INT4, fp16 activations): the K1 quantisation of the new K / V
+ * (demo/quantize_int4.cu:73-144, done by the reference in int4_kv.py:261-371 before every attention call) is part of the
+ * same launch — the CTA that owns the end of a head's key range rotates and quantises the new rows into the cache, reads
+ * them back with the rest of its keys, and commits the streaming ring when it has drained its pipeline; cache content
+ * and outputs are bit-identical to duo_rope_append + duo_attention + duo_stream_commit.  The very first chunk of a
+ * sequence must still go through the three calls on an fp16 layer: the reference attends the raw K / V there
+ * (demo/w8a8kv4_llama.py:229-238).
  */
+#define DUO_DECODE_MAX_Q_INT4 8
 DUO_API int duo_decode_fused(const duo_layer* layer, const duo_cache_state* st, const void* qkv, int64_t qkv_row_stride,
                              const void* cos, const void* sin, int32_t rope_mode, void* out, int32_t q_len, float scale,
                              void* workspace, size_t workspace_bytes, void* stream);

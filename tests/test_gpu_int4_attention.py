@@ -145,3 +145,54 @@ def test_w8a8kv4_attention_core_through_the_fused_qkv_boundary():
         ref, past = O.int4_attention_core(qr, kr, v, past, n_full, Hq // Hkv, sink, recent)
         assert_parity(out.view(1, S, Hq, D).float().cpu(), ref.float(), f"chunk of {S} at {pos}")
         pos += S
+
+
+@pytest.mark.parametrize("rope", ["none", "hf", "fp32"])
+@pytest.mark.parametrize("shape", ["gqa4", "mha", "b2"])
+def test_int4_one_launch_decode_is_bit_identical_to_three_launches(rope, shape):
+    """duo_decode_fused on an INT4 cache (RoPE + K1 quantise + append + attention + ring commit in one launch) against
+    duo_rope_append + duo_attention + duo_stream_commit on the same inputs: outputs and every cache tensor must hold
+    the same bits after every step (the two paths share the RoPE / K1 device functions).  Schedules cross the sink
+    boundary, wrap the ring and straddle split / tile boundaries of the retrieval cache."""
+    from duo_attention_b200.patch.w8a8kv4 import rope_tables_fp32
+
+    dev = torch.device("cuda:0")
+    Hq, Hkv, n_full, B, chunks = {
+        "gqa4": (8, 2, 1, 1, [3, 1, 1, 2, 1, 40, 1, 2, 1, 1, 2, 5000, 1, 2, 1, 1]),
+        "mha": (4, 4, 2, 1, [2, 1, 8, 7, 1, 3, 30, 5, 1, 8, 8, 8, 1]),
+        "b2": (8, 2, 2, 2, [130, 1, 2, 1, 1, 1, 2, 2, 1]),
+    }[shape]
+    sink, recent = 4, 12
+    mode = {"none": _C.ROPE_NONE, "hf": _C.ROPE_HF, "fp32": _C.ROPE_FP32}[rope]
+    caches = [DuoKVCache(1, Hq, Hkv, D, [n_full], B, sum(chunks) + 8, sink, recent, torch.float16, dev,
+                         stage_cap=max(chunks), kv_format="int4") for _ in range(2)]
+    g = torch.Generator().manual_seed(91)
+    pos, n_fused = 0, 0
+    for S in chunks:
+        qkv = torch.randn(B, S, (Hq + 2 * Hkv) * D, generator=g).to(torch.float16).to(dev)
+        cos = sin = None
+        if mode != _C.ROPE_NONE:
+            cos, sin = rope_tables_fp32(pos, S, D, 10000.0, 1.0, dev)
+            if mode == _C.ROPE_HF:
+                cos, sin = cos.to(torch.float16), sin.to(torch.float16)
+        outs = []
+        for cache, fused in zip(caches, (True, False)):
+            x = qkv.clone()
+            out = torch.empty(B, S, Hq, D, dtype=torch.float16, device=dev)
+            before = cache.launch_count
+            cache.attend(0, x, cos, sin, mode, out, fused=fused)
+            if fused and cache.launch_count - before == 1:
+                n_fused += 1
+                assert torch.equal(x, qkv), "the one-launch path must not modify qkv"
+            outs.append(out)
+        assert torch.equal(outs[0], outs[1]), f"outputs differ at chunk of {S} tokens (pos {pos})"
+        for name in caches[0].tensors[0]:
+            a, b = caches[0].tensors[0][name], caches[1].tensors[0][name]
+            if name.startswith("ring"):  # staging rows beyond the ring hold leftovers of the unfused path only
+                a, b = a[:, :, : caches[0].W], b[:, :, : caches[0].W]
+            else:
+                a, b = a[:, :, : pos + S], b[:, :, : pos + S]
+            assert torch.equal(a, b), f"cache tensor {name} differs after a chunk of {S} tokens (pos {pos})"
+        pos += S
+    G = Hq // Hkv
+    assert n_fused == sum(1 for i, S in enumerate(chunks) if i > 0 and S * G <= 8), "one-launch path not taken"
