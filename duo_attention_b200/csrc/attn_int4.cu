@@ -841,8 +841,11 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
       for (int hk = 0; hk < 2; ++hk) {
         const int key = wkey + mt * 16 + hk * 8 + g;
         const float ks = lds_half(sKs + 2 * key), kz = lds_half(sKz + 2 * key);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) sc[mt][hk * 2 + e] = ks * (sc[mt][hk * 2 + e] - qoff[e]) + kz * qsum[e];
+        // the two query rows of this lane as one packed pair: ks * (S_raw - qoff) + kz * qsum
+        float d0, d1, z0, z1;
+        add2(d0, d1, sc[mt][hk * 2], sc[mt][hk * 2 + 1], -qoff[0], -qoff[1]);
+        mul2(z0, z1, qsum[0], qsum[1], kz, kz);
+        fma2(sc[mt][hk * 2], sc[mt][hk * 2 + 1], d0, d1, ks, ks, z0, z1);
       }
     }
     if (need_mask) {
@@ -907,13 +910,14 @@ __global__ void __launch_bounds__(I4_THREADS, 4) duo_attn_int4_dec8_kernel(const
       for (int hk = 0; hk < 2; ++hk) {
         const int key = wkey + mt * 16 + hk * 8 + g;
         const float vs = lds_half(sVs + 2 * key), vz = lds_half(sVz + 2 * key);
-        const float p0 = fast_exp2(sc[mt][hk * 2 + 0] * p.scale_log2 - msc[0]);
-        const float p1 = fast_exp2(sc[mt][hk * 2 + 1] * p.scale_log2 - msc[1]);
-        l_run[0] += p0;
-        l_run[1] += p1;
-        pz_run[0] += p0 * vz;
-        pz_run[1] += p1 * vz;
-        const __half2 a = __floats2half2_rn(p0 * vs, p1 * vs);  // (key | rows 2t, 2t+1)
+        float x0, x1, a0, a1;
+        fma2(x0, x1, sc[mt][hk * 2 + 0], sc[mt][hk * 2 + 1], p.scale_log2, p.scale_log2, -msc[0], -msc[1]);
+        const float p0 = fast_exp2(x0);
+        const float p1 = fast_exp2(x1);
+        add2(l_run[0], l_run[1], l_run[0], l_run[1], p0, p1);
+        fma2(pz_run[0], pz_run[1], p0, p1, vz, vz, pz_run[0], pz_run[1]);
+        mul2(a0, a1, p0, p1, vs, vs);
+        const __half2 a = __floats2half2_rn(a0, a1);  // (key | rows 2t, 2t+1)
         pb[mt][hk] = movm_trans(*reinterpret_cast<const uint32_t*>(&a));  // -> (keys 2t, 2t+1 | row g)
       }
     }

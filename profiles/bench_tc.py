@@ -1,3 +1,6 @@
+"""Isolated tcgen05 prefill launch: one Llama-3-8B layer (32 q / 8 kv heads, n_full = 4), a 32,768-token chunk over 98,304
+cached tokens.  DUO_B200_LIB selects a tuning build (make -C duo_attention_b200/csrc variants); DUO_TC_REF=<file> saves the
+output of the first run and compares later runs against it (profiles/tc_variants.sh)."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.getcwd())
 import torch
@@ -20,11 +23,21 @@ def run():
 for _ in range(2): run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 4
+reps = int(os.environ.get("DUO_TC_REPS", "4"))
 e0.record()
 for _ in range(reps): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 pf = chunk * past + chunk * (chunk + 1) // 2; ps = chunk * W + chunk * (chunk + 1) // 2
 fl = 4.0 * D * G * (nf * pf + (Hkv - nf) * ps)
-print(os.environ.get("DUO_B200_LIB", "default"), f"{ms:.2f} ms  {fl/ms/1e9:.0f} TFLOP/s  checksum {out.float().abs().mean().item():.6f}")
+msg = f"{os.environ.get('DUO_B200_LIB', 'default')} {ms:.2f} ms  {fl/ms/1e9:.0f} TFLOP/s  checksum {out.float().abs().mean().item():.6f}"
+ref = os.environ.get("DUO_TC_REF")
+if ref:
+    if not os.path.exists(ref):
+        torch.save(out.cpu(), ref)
+    else:
+        base = torch.load(ref).to(dev).float()
+        d = (out.float() - base).abs()
+        bad = (d > 1e-3 + 1e-2 * base.abs()).sum().item()
+        msg += f"  vs base: max|d| {d.max().item():.3e} mean|d| {d.mean().item():.3e} outside(1e-2,1e-3) {bad} of {d.numel()}"
+print(msg)
