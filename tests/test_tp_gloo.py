@@ -1,4 +1,4 @@
-"""World-size-2 gloo (CPU) tests of the head-parallel host logic: planning, weight slicing and the one
+"""World-size-2 and -4 gloo (CPU) tests of the head-parallel host logic: planning, weight slicing and the one
 all-reduce per layer.  The attention op itself is injected (oracle, CPU) — on the GPU box it is the CUDA path."""
 import os
 
@@ -79,13 +79,13 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_sharded_layers_sum_to_the_single_process_result():
-    world = 2
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_layers_sum_to_the_single_process_result(world):
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: True, 1: True}
+    assert dict(ret) == {r: True for r in range(world)}
 
 
 def _reshard_worker(rank, world, port, ret):
@@ -115,12 +115,12 @@ def _reshard_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_reshard_from_head_parallel_to_sequence_sharded_layout():
+@pytest.mark.parametrize("world", [2, 4])
+def test_reshard_from_head_parallel_to_sequence_sharded_layout(world):
     """tp.reshard_heads_to_seq (point-to-point, what DuoSeqShardKVCache.load_from_head_parallel runs per layer):
     every rank ends up with its block-cyclic position slice of EVERY retrieval head, in reordered head order."""
-    world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 31500 + (os.getpid() % 2000)
+    port = 31500 + (os.getpid() % 2000) + world
     mp.spawn(_reshard_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: True, 1: True}
+    assert dict(ret) == {r: True for r in range(world)}
