@@ -20,6 +20,10 @@
 // Tiles (64 keys: 4 KB K + 4 KB V + 4 x 128 B scale/zero = 8.5 KB instead of 32 KB) are fetched with 16 B
 // cp.async (zero-fill beyond the valid rows) into a 4-stage ring.  Same work decomposition, masks, split-KV merge
 // and variants as attn_mma.cu.  Activations are fp16 (the reference's INT4 demo runs in fp16).
+//
+// The decode kernel (duo_attn_int4_dec8_kernel, group x q_len <= 8) swaps the operand roles (keys are the MMA M) and, as
+// duo_decode_fused, is the whole decode step of a layer in one launch: q RoPE in registers, RoPE + K1 quantisation +
+// append of the new K / V by the CTA that reads those rows, ring commit by the streaming-head CTA.
 #include <cstdlib>
 
 #include "duo_common.cuh"

@@ -19,6 +19,11 @@
 //
 // Masks: retrieval heads use bottom-right causal over [cache | chunk]; streaming heads attend the
 // live sink/ring slots (validity table in smem) plus the staged chunk causally — see duo_b200.h.
+//
+// What bounds it (measured): the tile period is the serial timeline of the ISSUER thread — a
+// tcgen05.mma issue blocks for the duration of the MMA (QK^T ~60 cycles, PV ~96) and every mbarrier test costs it
+// ~100 cycles — not the softmax (re-arranging it changes nothing).  Hence mbar_wait3 (tests in flight together) on the
+// issuer and packed fp32 pairs (FFMA2 / FADD2) in the softmax fast path; ncu tensor pipe 61 %.
 #include <cstdlib>
 
 #include "duo_common.cuh"
