@@ -39,6 +39,19 @@ def test_header_symbols_exported_and_bound():
     assert exported == set(names), exported ^ set(names)
 
 
+def test_header_constants_match_the_binding():
+    """#define values of the header == the integers the ctypes binding (and through it the host code) uses."""
+    from duo_attention_b200 import _C
+
+    src = open(HDR).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(DUO_\w+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\s*(?:/|$)", src, re.M)}
+    want = dict(DUO_DECODE_MAX_Q=_C.DECODE_MAX_Q, DUO_DECODE_MAX_Q_INT4=_C.DECODE_MAX_Q_INT4)
+    for k, v in want.items():
+        assert defs.get(k) == v, (k, defs.get(k), v)
+    assert "FFMA2" in subprocess.run(["cuobjdump", "-sass", _ensure_built().LIB_PATH], capture_output=True,
+                                     text=True, timeout=300).stdout, "packed fp32 pairs missing from the SASS"
+
+
 def test_host_only_entry_points():
     _C = _ensure_built()
     lib = _C.load()
